@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched step() hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W              # our arm (default)
+    python bench.py --impl reference --gpus 1 --steps K --warmup W
+    torchrun ... bench.py --gpus N ...                          # one rank per GPU
+
+A "step" is one sync step of one batch: every env of the pool advances once.  Workload at
+N=1: BASELINE.json configs[1], CartPole-v1 with num_envs=65536 on one B200 (weak scaling for
+N>1: 65536 envs per GPU, env ids sharded, one NCCL all-gather of the output columns per
+step).  `value` is measured with actions and outputs resident in HBM (device-resident C-ABI
+path, K single-step launches replayed from a CUDA graph); `e2e` is the same metric through
+the reference-facing API (envpool_b200.make(...).step(numpy)) with host buffers, H2D/D2H
+inside the timed region.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# task id -> (engine task, registered max_episode_steps, iopt, #discrete actions or None)
+TASKS = {
+    "CartPole-v1": ("CartPole", 500, -1, 2),
+    "Pendulum-v1": ("Pendulum", 200, 1, None),
+    "Acrobot-v1": ("Acrobot", 500, -1, 3),
+    "MountainCar-v0": ("MountainCar", 200, -1, 3),
+    "FrozenLake-v1": ("FrozenLake", 100, 4, 4),
+    "Catch-v0": ("Catch", -1, -1, 3),
+    "Taxi-v3": ("Taxi", 200, -1, 6),
+    "HalfCheetah-v4": ("HalfCheetah", 1000, -1, None),
+}
+METRIC = "env steps/sec (whole box)"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the bench runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.samples = []
+        self.proc = None
+        self.t = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._pump, daemon=True)
+        self.t.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.samples:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                smax = float(parts[1])
+                if t0 - 0.05 <= ts <= t1 + 0.05:
+                    sm.append(float(parts[0]))
+                    power.append(float(parts[2]))
+                    for nm, v in zip(names, parts[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nm)
+            except ValueError:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples_under_load": len(sm),
+                "power_w_max": max(power) if power else None}
+
+
+def make_action_stream(torch, task, n, device, min_bytes):
+    """[T, N, ...] synthetic actions on the device, larger than L2 so no row is re-read
+    while it could still be cached."""
+    eng, _, _, nact = TASKS[task]
+    row = n * (48 if eng == "HalfCheetah" else 4)
+    T = max(64, -(-min_bytes // row))
+    T = -(-T // 64) * 64
+    g = torch.Generator(device=device)
+    g.manual_seed(1)
+    if eng == "HalfCheetah":
+        a = torch.rand((T, n, 6), generator=g, device=device, dtype=torch.float64) * 2 - 1
+    elif nact is None:
+        a = (torch.rand((T, n, 1), generator=g, device=device, dtype=torch.float32) * 4 - 2)
+    else:
+        a = torch.randint(0, nact, (T, n), generator=g, device=device, dtype=torch.int32)
+    return a
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the env-step engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from envpool_b200 import _capi
+
+    eng, ms, iopt, _ = TASKS[args.task]
+    n = args.num_envs
+    pool = _capi.CPool(eng, n, seed=0, max_episode_steps=ms, iopt=iopt, device=local,
+                       precision=args.precision, env_id_offset=rank * n)
+    stream = torch.cuda.ExternalStream(pool.stream, device=dev)
+    actions = make_action_stream(torch, args.task, n, dev, 2 * L2_BYTES)
+    T = actions.shape[0]
+    K, W = args.steps, args.warmup
+    use_graph = not args.no_graph
+
+    # multi-GPU exchange step: all-gather every output column into the full [G*n, ...] batch
+    gathered = None
+    if world > 1:
+        outs = pool.outputs_torch()
+        gathered = {k: torch.empty((world * n,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
+                    for k, v in outs.items()}
+
+    def run_steps(count):
+        """`count` sync steps; actions cycle through the whole [T, N] stream in order."""
+        if world == 1:
+            q, r = divmod(count, T)
+            for _ in range(q):
+                pool.step_many_device(actions, 0, T, use_graph=use_graph)
+            if r:
+                pool.step_many_device(actions, 0, r, use_graph=use_graph)
+        else:
+            outs = pool.outputs_torch()
+            for k in range(count):
+                pool.step_device(actions[k % T])
+                with torch.cuda.stream(stream):
+                    for name, v in outs.items():
+                        dist.all_gather_into_tensor(gathered[name], v)
+
+    pool.reset_device()
+    pool.sync()
+    sampler = ClockSampler(local)
+    if rank == 0 and not args.profile:
+        sampler.start()
+    t_load0 = time.time()
+    # warm-up (also captures the CUDA graphs); stretched so that clocks are sampled under
+    # load for ~1 s before the timed region starts
+    run_steps(W)
+    pool.sync()
+    if not args.profile:
+        t_w = time.time()
+        while True:  # also instantiates every CUDA graph the timed region will replay
+            run_steps(K)
+            pool.sync()
+            if time.time() - t_w >= 1.0:
+                break
+    launches0 = pool.launch_count
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    run_steps(K)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_load1 = time.time()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = pool.launch_count - launches0
+    if world > 1:
+        tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    clocks = sampler.stop(t_load0, t_load1) if rank == 0 and not args.profile else None
+    ms_per_step = ms_total / K
+    value = n * world * K / (ms_total * 1e-3)
+
+    result = None
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        bpe = pool.bytes_per_env_step
+        achieved = bpe * n / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(f"{args.task}:{n}:{args.precision}")
+        except Exception:
+            pass
+        result = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.precision == "f64" else "f32", "data": "synthetic",
+            "config": {
+                "workload": f"{args.task} sync num_envs={n} per GPU x {world} GPU "
+                            f"(BASELINE.json configs[1])",
+                "api": "device-resident C-ABI single-step kernel, one launch per step"
+                       + (", CUDA-graph replay" if use_graph and world == 1 else "")
+                       + (", + NCCL all-gather of every output column per step"
+                          if world > 1 else ""),
+                "l2": f"action stream {actions.numel() * actions.element_size() >> 20} MiB "
+                      f"> 126 MiB L2, each row read once per cycle; the recurrent env state "
+                      f"and output slab ({bpe * n >> 10} KiB) stay on chip by construction "
+                      f"at this num_envs",
+                "precision": args.precision, "seed": 0,
+            },
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "bytes_per_env_step": bpe, "peak_source": peak_src,
+                         "kernel": "step_kernel<%s>" % eng},
+            "clocks": clocks,
+        }
+    # ---- e2e through the public API with host buffers --------------------------------
+    if not args.profile:
+        e2e = run_e2e(args, torch, local, rank, world)
+        if rank == 0:
+            result["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.profile and not args.no_cpu:
+        result["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_seconds)
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, local, rank, world):
+    """Same metric through envpool_b200.make(...).step(numpy): per step the action batch is
+    copied host->device (via pinned staging) and every state column comes back device->host
+    into a pinned slab that the returned numpy arrays view."""
+    import envpool_b200
+
+    eng, ms, iopt, nact = TASKS[args.task]
+    n = args.num_envs
+    env = envpool_b200.make(args.task, env_type="gymnasium", num_envs=n, seed=0,
+                            device=local, precision=args.precision, env_id_offset=rank * n)
+    rng = np.random.default_rng(1)
+    Ta = 64
+    if eng == "HalfCheetah":
+        acts = rng.uniform(-1, 1, size=(Ta, n, 6))
+    elif nact is None:
+        acts = rng.uniform(-2, 2, size=(Ta, n, 1)).astype(np.float32)
+    else:
+        acts = rng.integers(0, nact, size=(Ta, n)).astype(np.int32)
+    env.reset()
+    E = int(min(max(args.steps, 50), 400))
+    for t in range(20):
+        env.step(acts[t % Ta])
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for t in range(E):
+        obs, rew, term, trunc, info = env.step(acts[t % Ta])
+        checksum += float(rew[0])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([dt], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    dp = env.device_pool
+    return {"value": n * world * E / dt, "unit": "env-steps/s", "steps": E,
+            "h2d_bytes_per_step": int(acts[0].nbytes), "d2h_bytes_per_step": int(dp.slab_bytes),
+            "ms_per_step": dt / E * 1e3,
+            "api": "envpool_b200.make(task,'gymnasium').step(numpy actions) -> numpy"}
+
+
+def cpu_baseline(args, budget_s=15.0, steps=None, warmup=3):
+    """The reference's own CPU thread pool (oracle/_ref = its AsyncEnvPool + env headers
+    compiled from /root/reference) timed on this box's host cores; falls back to the scalar
+    oracle port when _ref is absent."""
+    eng, ms, iopt, nact = TASKS[args.task]
+    n = args.num_envs
+    rng = np.random.default_rng(1)
+    from oracle import ref_lib
+
+    cores = os.cpu_count() or 1
+    if ref_lib.available() and eng != "HalfCheetah":
+        Ta = 16
+        if nact is None:
+            acts = rng.uniform(-2, 2, size=(Ta, n, 1)).astype(np.float32)
+        else:
+            acts = rng.integers(0, nact, size=(Ta, n)).astype(np.int32)
+        pool = ref_lib.RefPool(eng, n, seed=0, max_episode_steps=ms, iopt=iopt, num_threads=0)
+        if steps is None:
+            probe = pool.bench(acts, 1, 3) / 3
+            steps = int(min(max(budget_s / max(probe, 1e-6), 5), 5000))
+        dt = pool.bench(acts, warmup, steps)
+        pool.close()
+        return {"value": n * steps / dt, "unit": "env-steps/s", "cores": cores,
+                "kind": "reference", "ms_per_step": dt / steps * 1e3,
+                "sample": f"{steps} sync steps of the same {n}-env batch workload, "
+                          f"AsyncEnvPool num_threads=min(batch, {cores} hw threads)"}
+    from oracle.oracle_lib import OraclePool
+
+    pool = OraclePool(eng, n, seed=0, max_episode_steps=ms, iopt=iopt)
+    if eng == "HalfCheetah":
+        acts = rng.uniform(-1, 1, size=(4, n, 6))
+    elif nact is None:
+        acts = rng.uniform(-2, 2, size=(4, n, 1)).astype(np.float32)
+    else:
+        acts = rng.integers(0, nact, size=(4, n)).astype(np.int32)
+    pool.reset()
+    t0 = time.perf_counter()
+    pool.step(acts[0])
+    probe = time.perf_counter() - t0
+    if steps is None:
+        steps = int(min(max(budget_s / max(probe, 1e-6), 2), 2000))
+    t0 = time.perf_counter()
+    for t in range(steps):
+        pool.step(acts[t % 4])
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
+            "ms_per_step": dt / steps * 1e3,
+            "sample": f"{steps} sync steps of the same {n}-env batch, scalar C port"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    K, W = args.steps, args.warmup
+    # bound the run to a few minutes: one reference step of 65536 envs is tens of ms
+    cb = cpu_baseline(args, steps=K, warmup=W)
+    n = args.num_envs
+    out = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "env-steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": cb["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{args.task} sync num_envs={n} (BASELINE.json configs[1]) on "
+                               f"the reference CPU thread pool, {cb['cores']} host threads",
+                   "note": "the reference has no GPU path; one process uses every host core, "
+                           "so the value does not scale with --gpus"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=2000)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--task", default="CartPole-v1", choices=sorted(TASKS))
+    ap.add_argument("--num-envs", type=int, default=65536, help="envs per GPU")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--profile", action="store_true",
+                    help="kernel loop only (for ncu): no clocks sampler, e2e or cpu legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 20000 and args.warmup == 2000:
+            args.steps, args.warmup = 200, 5
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,144 @@
+"""Global env registry: mirror of envpool/registration.py (register / make / make_dm /
+make_gym / make_gymnasium / make_spec / list_all_envs) for the accelerated tasks.
+
+Engine-only keyword arguments (not part of the reference config tuple) are accepted by
+make(): device=<cuda ordinal>, precision="f64"|"f32", env_id_offset=<global id of env 0>.
+"""
+from __future__ import annotations
+
+import importlib
+from collections.abc import Sequence
+from typing import Any, Dict, List, Tuple
+
+import numpy as np
+
+ENGINE_KWARGS = ("device", "precision", "env_id_offset")
+
+
+class EnvRegistry:
+    def __init__(self) -> None:
+        self.specs: Dict[str, Tuple[str, str, Dict[str, Any]]] = {}
+        self.envpools: Dict[str, Dict[str, Tuple[str, str]]] = {}
+
+    def register(self, task_id: str, import_path: str, spec_cls: str, dm_cls: str,
+                 gymnasium_cls: str, aliases: Sequence[str] = (), **kwargs: Any) -> None:
+        if "base_path" not in kwargs:
+            kwargs["base_path"] = "envpool"
+        for alias in (task_id, *aliases):
+            assert alias not in self.specs
+            self.specs[alias] = (import_path, spec_cls, dict(kwargs))
+            self.envpools[alias] = {"dm": (import_path, dm_cls),
+                                    "gymnasium": (import_path, gymnasium_cls)}
+
+    # -- seed handling, envpool/registration.py:303-336 --------------------------------
+    @staticmethod
+    def _assert_int32_seed(seed: Any) -> None:
+        assert -(2**31) <= seed < 2**31, f"Seed should be in range of int32, got {seed}"
+
+    @staticmethod
+    def _is_env_seed_sequence(seed: Any) -> bool:
+        return (isinstance(seed, Sequence) and not isinstance(seed, (str, bytes))) or \
+            isinstance(seed, np.ndarray)
+
+    def _normalize_env_seed(self, seed: Any, num_envs: int) -> List[int]:
+        if isinstance(seed, np.ndarray):
+            assert seed.ndim == 1, f"`seed` as an array must be 1-dimensional, got shape {seed.shape}"
+            seed = seed.tolist()
+        else:
+            seed = list(seed)
+        assert len(seed) == num_envs, (
+            "When `seed` is a sequence, its length must match `num_envs`, "
+            f"got len(seed) = {len(seed)} and num_envs = {num_envs}")
+        out = [int(s) for s in seed]
+        for s in out:
+            self._assert_int32_seed(s)
+        return out
+
+    def _make_env_spec(self, task_id: str, **make_kwargs: Any):
+        import_path, spec_cls, kwargs = self.specs[task_id]
+        kwargs = {**kwargs, **make_kwargs}
+        for unsupported in ("from_pixels", "render_mode", "render_env_id", "render_width",
+                            "render_height", "render_camera_id"):
+            if kwargs.pop(unsupported, None):
+                raise ValueError(f"{unsupported} is outside the accelerated step path")
+        if "seed" in kwargs:
+            if self._is_env_seed_sequence(kwargs["seed"]):
+                assert "env_seed" not in kwargs, (
+                    "Pass either `seed` as an int or seed list, or `env_seed`, but not both.")
+                kwargs["env_seed"] = self._normalize_env_seed(kwargs["seed"],
+                                                              kwargs.get("num_envs", 1))
+                kwargs["seed"] = 0
+            else:
+                self._assert_int32_seed(kwargs["seed"])
+        if "env_seed" in kwargs:
+            kwargs["env_seed"] = self._normalize_env_seed(kwargs["env_seed"],
+                                                          kwargs.get("num_envs", 1))
+        if "num_envs" in kwargs:
+            assert kwargs["num_envs"] >= 1
+        if "batch_size" in kwargs:
+            assert 0 <= kwargs["batch_size"] <= kwargs["num_envs"]
+        if "max_num_players" in kwargs:
+            assert 1 <= kwargs["max_num_players"]
+        cls = getattr(importlib.import_module(import_path), spec_cls)
+        config = cls.gen_config(**kwargs)
+        return cls(config)
+
+    def make(self, task_id: str, env_type: str, **kwargs: Any):
+        if "gym_reset_return_info" not in kwargs:
+            kwargs["gym_reset_return_info"] = True
+        if not kwargs["gym_reset_return_info"]:
+            raise ValueError("EnvPool's gym API now follows gymnasium reset semantics and "
+                             "always returns an info dictionary after resets.")
+        assert task_id in self.specs, (
+            f"{task_id} is not supported, `envpool.list_all_envs()` may help.")
+        assert env_type in ["dm", "gymnasium"]
+        engine_kwargs = {k: kwargs.pop(k) for k in ENGINE_KWARGS if k in kwargs}
+        spec = self._make_env_spec(task_id, **kwargs)
+        import_path, envpool_cls = self.envpools[task_id][env_type]
+        return getattr(importlib.import_module(import_path), envpool_cls)(spec, **engine_kwargs)
+
+    def make_dm(self, task_id: str, **kwargs: Any):
+        return self.make(task_id, "dm", **kwargs)
+
+    def make_gymnasium(self, task_id: str, **kwargs: Any):
+        return self.make(task_id, "gymnasium", **kwargs)
+
+    def make_spec(self, task_id: str, **make_kwargs: Any):
+        for k in ENGINE_KWARGS:
+            make_kwargs.pop(k, None)
+        return self._make_env_spec(task_id, **make_kwargs)
+
+    def list_all_envs(self) -> List[str]:
+        return list(self.specs.keys())
+
+
+registry = EnvRegistry()
+register = registry.register
+
+
+def make(task_id: str, env_type: str, **kwargs: Any):
+    if env_type == "dm":
+        return registry.make(task_id, "dm", **kwargs)
+    if env_type in ("gym", "gymnasium"):
+        return registry.make(task_id, "gymnasium", **kwargs)
+    raise AssertionError("env_type should be one of 'dm', 'gym', or 'gymnasium'.")
+
+
+def make_dm(task_id: str, **kwargs: Any):
+    return registry.make_dm(task_id, **kwargs)
+
+
+def make_gym(task_id: str, **kwargs: Any):
+    return make_gymnasium(task_id, **kwargs)
+
+
+def make_gymnasium(task_id: str, **kwargs: Any):
+    return registry.make_gymnasium(task_id, **kwargs)
+
+
+def make_spec(task_id: str, **kwargs: Any):
+    return registry.make_spec(task_id, **kwargs)
+
+
+def list_all_envs() -> List[str]:
+    return registry.list_all_envs()

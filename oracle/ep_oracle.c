@@ -832,4 +832,17 @@ int epo_key_row_elems(const epo_pool* p, int k) { return p->keys[k].row_elems; }
 const void* epo_key_data(const epo_pool* p, int k) { return p->keys[k].data; }
 int epo_action_elem_size(const epo_pool* p) { return p->act_elem_size; }
 int epo_action_row_elems(const epo_pool* p) { return p->act_row_elems; }
+void epo_get_state(const epo_pool* p, int eid, double* s5, int* done, int* cur) {
+  const epo_env* e = &p->envs[eid];
+  for (int k = 0; k < 5; ++k) s5[k] = e->s[k];
+  *done = e->done;
+  *cur = e->current_step;
+}
+void epo_set_state(epo_pool* p, int eid, const double* s5, int done, int cur) {
+  epo_env* e = &p->envs[eid];
+  for (int k = 0; k < 5; ++k) e->s[k] = s5[k];
+  e->done = done;
+  e->current_step = cur;
+  e->elapsed = cur;
+}
 uint32_t epo_debug_draw(epo_pool* p, int eid) { return rng_next(&p->envs[eid].rng); }

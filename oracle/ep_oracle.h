@@ -57,6 +57,11 @@ int epo_key_row_elems(const epo_pool* p, int k);
 const void* epo_key_data(const epo_pool* p, int k);
 int epo_action_elem_size(const epo_pool* p);
 int epo_action_row_elems(const epo_pool* p);
+/* teacher forcing (tests): read / overwrite one env's continuous state s[0..4], its
+ * done flag and its step counters (current_step_ == elapsed_step_ for every env that has
+ * one) without touching its RNG */
+void epo_get_state(const epo_pool* p, int eid, double* s5, int* done, int* cur);
+void epo_set_state(epo_pool* p, int eid, const double* s5, int done, int cur);
 /* raw engine draw from env `eid`'s std::mt19937 (for RNG known-answer tests) */
 uint32_t epo_debug_draw(epo_pool* p, int eid);
 

@@ -54,6 +54,8 @@ def lib():
         L.epo_key_data.argtypes = [vp, ci]
         L.epo_action_elem_size.argtypes = [vp]
         L.epo_action_row_elems.argtypes = [vp]
+        L.epo_get_state.argtypes = [vp, ci, vp, vp, vp]
+        L.epo_set_state.argtypes = [vp, ci, vp, ci, ci]
         L.epo_debug_draw.restype = ctypes.c_uint32
         L.epo_debug_draw.argtypes = [vp, ci]
         _lib = L
@@ -137,6 +139,16 @@ class OraclePool:
         ids = np.ascontiguousarray(env_ids, dtype=np.int32)
         lib().epo_step(self.h, a.ctypes.data, ids.ctypes.data, len(ids))
         return self._collect(len(ids))
+
+    def set_state(self, eid, s5, done, cur):
+        buf = (ctypes.c_double * 5)(*[float(x) for x in s5])
+        lib().epo_set_state(self.h, eid, buf, int(done), int(cur))
+
+    def get_state(self, eid):
+        buf = (ctypes.c_double * 5)()
+        d, c = ctypes.c_int(), ctypes.c_int()
+        lib().epo_get_state(self.h, eid, buf, ctypes.byref(d), ctypes.byref(c))
+        return list(buf), d.value, c.value
 
     def draw(self, eid):
         return lib().epo_debug_draw(self.h, eid)
