@@ -167,12 +167,13 @@ def run_ours(args):
             if r:
                 pool.step_many_device(actions, 0, r, use_graph=use_graph)
         else:
+            from envpool_b200.sharded import all_gather_columns
+
             outs = pool.outputs_torch()
             for k in range(count):
                 pool.step_device(actions[k % T])
                 with torch.cuda.stream(stream):
-                    for name, v in outs.items():
-                        dist.all_gather_into_tensor(gathered[name], v)
+                    all_gather_columns(outs, gathered)
 
     pool.reset_device()
     pool.sync()
@@ -230,8 +231,9 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if args.precision == "f64" else "f32", "data": "synthetic",
             "config": {
-                "workload": f"{args.task} sync num_envs={n} per GPU x {world} GPU "
-                            f"(BASELINE.json configs[1])",
+                "workload": f"{args.task} sync num_envs={n} per GPU x {world} GPU"
+                            + (" (BASELINE.json configs[1])"
+                               if (args.task, n) == ("CartPole-v1", 65536) else ""),
                 "api": "device-resident C-ABI single-step kernel, one launch per step"
                        + (", CUDA-graph replay" if use_graph and world == 1 else "")
                        + (", + NCCL all-gather of every output column per step"
@@ -249,6 +251,11 @@ def run_ours(args):
                          "kernel": "step_kernel<%s>" % eng},
             "clocks": clocks,
         }
+    # ---- fused rollout API: T steps per launch, state in registers ----------------------
+    if world == 1 and not args.profile:
+        ro = run_rollout(args, torch, pool, actions, dev)
+        if rank == 0:
+            result["rollout"] = ro
     # ---- e2e through the public API with host buffers --------------------------------
     if not args.profile:
         e2e = run_e2e(args, torch, local, rank, world)
@@ -261,6 +268,42 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_rollout(args, torch, pool, actions, dev):
+    """epb_rollout_device: T consecutive sync steps of all envs in ONE launch (the fused
+    random-action rollout of north_star); every step's outputs are written to [T, N, ...]
+    arrays in HBM, actions are read from the [T, N] stream, env state lives in registers."""
+    n = pool.n
+    out_row = sum(k.row_bytes for k in pool.keys)
+    T = int(max(4, min(64, (2 << 30) // max(1, out_row * n), actions.shape[0])))
+    tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.float32): torch.float32,
+           np.dtype(np.float64): torch.float64, np.dtype(np.bool_): torch.bool}
+    cols = [torch.empty((T, n) + k.shape, dtype=tdt[k.dtype], device=dev) for k in pool.keys]
+    stream = torch.cuda.ExternalStream(pool.stream, device=dev)
+    launches = max(3, min(200, args.steps // T))
+    nrows = actions.shape[0] // T
+    for i in range(3):
+        pool.rollout_device(actions[(i % nrows) * T:], T, cols)
+    pool.sync()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(launches):
+        pool.rollout_device(actions[(i % nrows) * T:], T, cols)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    steps = launches * T
+    state_bytes = pool.bytes_per_env_step - pool.action_key.row_bytes - out_row
+    bpe = pool.action_key.row_bytes + out_row + state_bytes / T
+    peak, _ = measured_peak_hbm()
+    achieved = bpe * n * steps / (ms * 1e-3) / 1e9
+    return {"value": n * steps / (ms * 1e-3), "unit": "env-steps/s", "T_per_launch": T,
+            "launches": launches, "ms_per_step": ms / steps,
+            "bytes_per_env_step": bpe,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak},
+            "api": "epb_rollout_device: T steps per launch, outputs [T,N,...] written to HBM"}
 
 
 def run_e2e(args, torch, local, rank, world):

@@ -359,6 +359,8 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
     return fail(EPB_ERR_INVALID, "FrozenLake size must be 4 or 8");
   }
   if (kind == EPB_HALF_CHEETAH) {
+    p->precision = 0;  // HalfCheetah physics is fp64 only
+    p->real_size = 8;
     p->mjc = mjc_pool_create(p->N, p->precision, cfg->frame_skip > 0 ? cfg->frame_skip : 5,
                              cfg->ctrl_cost_weight >= 0 ? cfg->ctrl_cost_weight : 0.1,
                              cfg->forward_reward_weight >= 0 ? cfg->forward_reward_weight : 1.0,
@@ -441,6 +443,7 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
   for (const Key& k : p->keys) b += k.row_bytes;
   if (kind == EPB_FROZEN_LAKE || (kind == EPB_CLIFF_WALKING && iopt)) b += 16 + 8;
   if (kind == EPB_NCHAIN) b += 32 + 8;
+  if (kind == EPB_HALF_CHEETAH) b -= 2 * (32 - 27) * 8;  // 27 of the 32-double record are live
   p->bytes_per_step = b;
   *out = p;
   return EPB_OK;

@@ -58,8 +58,10 @@ struct CartPole {
   }
   static __device__ __forceinline__ void reset(const StateView&, State& s, Mt* rng,
                                                StepOut& so) {
+    double v[4];
+    rng->uniform_real_batch<4>(-0.05, 0.05, v);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s.v[k] = (R)rng->uniform_real(-0.05, 0.05);
+    for (int k = 0; k < 4; ++k) s.v[k] = (R)v[k];
     so.reward = 0.0f;
   }
   static __device__ __forceinline__ void step(const StateView& sv, State& s, Act act, int cur,
@@ -111,8 +113,12 @@ struct Pendulum {
   }
   static __device__ __forceinline__ void reset(const StateView&, State& s, Mt* rng,
                                                StepOut& so) {
-    s.v[0] = (R)rng->uniform_real(-M_PI, M_PI);
-    s.v[1] = (R)rng->uniform_real(-1, 1);
+    uint32_t d[4];  // two uniform_real draws (different ranges), one round trip
+    rng->next_batch<4>(d);
+    s.v[0] = (R)__dadd_rn(__dmul_rn(Mt::canonical_from(d[0], d[1]), __dsub_rn(M_PI, -M_PI)),
+                          -M_PI);
+    s.v[1] = (R)__dadd_rn(__dmul_rn(Mt::canonical_from(d[2], d[3]), __dsub_rn(1.0, -1.0)),
+                          -1.0);
     so.reward = 0.0f;
   }
   static __device__ __forceinline__ void step(const StateView& sv, State& s, Act act, int cur,
@@ -199,8 +205,10 @@ struct Acrobot {
   }
   static __device__ __forceinline__ void reset(const StateView&, State& s, Mt* rng,
                                                StepOut& so) {
+    double v[4];
+    rng->uniform_real_batch<4>(-0.1, 0.1, v);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s.v[k] = (R)rng->uniform_real(-0.1, 0.1);
+    for (int k = 0; k < 4; ++k) s.v[k] = (R)v[k];
     so.reward = 0.0f;
   }
   static __device__ __forceinline__ void step(const StateView& sv, State& s, Act act, int cur,

@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace epb {
 
@@ -58,6 +59,10 @@ struct Mt {
   int idx;
   __device__ __forceinline__ Mt(const StateView& sv, int eid)
       : base(sv.mt + eid), stride(sv.n_envs), idx(sv.mt_idx[eid]) {}
+  // idx already loaded by the caller (issued together with the env-state loads so the
+  // draw does not pay a second dependent round trip)
+  __device__ __forceinline__ Mt(const StateView& sv, int eid, int idx_)
+      : base(sv.mt + eid), stride(sv.n_envs), idx(idx_) {}
   __device__ __forceinline__ uint32_t next() {
     int i = idx;
     int i1 = (i + 1 == kMtN) ? 0 : i + 1;
@@ -77,19 +82,72 @@ struct Mt {
   }
   __device__ __forceinline__ void save(const StateView& sv, int eid) { sv.mt_idx[eid] = idx; }
 
-  // std::generate_canonical<double,53> (libstdc++ 13 bits/random.tcc:3349-3381).
-  // Explicit _rn intrinsics: never contracted into an FMA, whatever the TU's flags.
-  __device__ __forceinline__ double canonical() {
-    double g1 = (double)next();
-    double g2 = (double)next();
-    double sum = __dadd_rn(g1, __dmul_rn(g2, 4294967296.0));
+  // K consecutive draws in ONE memory round trip.  Regenerating word i needs the current
+  // words i, i+1 and i+397; for K <= 226 none of those is itself regenerated earlier in the
+  // same batch except word i+1, whose *old* value is what the recurrence wants -- so all
+  // 2K+1 loads can be issued together (memory-level parallelism instead of K dependent
+  // DRAM latencies), then the K new words are stored.  Same sequence as K next() calls.
+  template <int K>
+  __device__ __forceinline__ void next_batch(uint32_t (&out)[K]) {
+    static_assert(K >= 1 && K <= 64, "batch too large");
+    uint32_t w[K + 1], m[K];
+    const int i = idx;
+#pragma unroll
+    for (int k = 0; k <= K; ++k) {
+      int j = i + k;
+      j = j >= kMtN ? j - kMtN : j;
+      w[k] = base[(int64_t)j * stride];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      int j = i + k + kMtM;
+      j = j >= kMtN ? j - kMtN : j;
+      j = j >= kMtN ? j - kMtN : j;
+      m[k] = base[(int64_t)j * stride];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      uint32_t y = (w[k] & 0x80000000u) | (w[k + 1] & 0x7fffffffu);
+      uint32_t v = m[k] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      int j = i + k;
+      j = j >= kMtN ? j - kMtN : j;
+      base[(int64_t)j * stride] = v;
+      v ^= (v >> 11);
+      v ^= (v << 7) & 0x9d2c5680u;
+      v ^= (v << 15) & 0xefc60000u;
+      v ^= (v >> 18);
+      out[k] = v;
+    }
+    int j = i + K;
+    idx = j >= kMtN ? j - kMtN : j;
+  }
+
+  // std::generate_canonical<double,53> (libstdc++ 13 bits/random.tcc:3349-3381) from two
+  // engine outputs.  Explicit _rn intrinsics: never contracted into an FMA, whatever the
+  // TU's flags.
+  static __device__ __forceinline__ double canonical_from(uint32_t d1, uint32_t d2) {
+    double sum = __dadd_rn((double)d1, __dmul_rn((double)d2, 4294967296.0));
     double ret = __dmul_rn(sum, 5.421010862427522170037e-20);  // exact: / 2^64
     if (ret >= 1.0) ret = 0.99999999999999988897769753748;     // nextafter(1,0)
     return ret;
   }
+  __device__ __forceinline__ double canonical() {
+    uint32_t d[2];
+    next_batch<2>(d);
+    return canonical_from(d[0], d[1]);
+  }
   // std::uniform_real_distribution<double>(a,b)
   __device__ __forceinline__ double uniform_real(double a, double b) {
     return __dadd_rn(__dmul_rn(canonical(), __dsub_rn(b, a)), a);
+  }
+  // NC consecutive uniform_real(a,b) draws, one memory round trip
+  template <int NC>
+  __device__ __forceinline__ void uniform_real_batch(double a, double b, double (&out)[NC]) {
+    uint32_t d[2 * NC];
+    next_batch<2 * NC>(d);
+#pragma unroll
+    for (int k = 0; k < NC; ++k)
+      out[k] = __dadd_rn(__dmul_rn(canonical_from(d[2 * k], d[2 * k + 1]), __dsub_rn(b, a)), a);
   }
   // std::uniform_int_distribution<int>(a,b): Lemire (bits/uniform_int_dist.h:252-282)
   __device__ __forceinline__ int uniform_int(int a, int b) {
@@ -100,6 +158,44 @@ struct Mt {
       uint32_t threshold = (0u - range) % range;
       while (low < threshold) {
         product = (uint64_t)next() * (uint64_t)range;
+        low = (uint32_t)product;
+      }
+    }
+    return a + (int)(product >> 32);
+  }
+};
+
+// K uniform_int draws with the engine words fetched in one round trip.  Lemire's method
+// almost never rejects (probability range/2^32 per draw); when it does, the extra words
+// come from sequential next() calls after the batch, so the word order is unchanged.
+template <int K>
+struct MtIntBatch {
+  Mt& rng;
+  uint32_t words[K];
+  int cursor;
+  __device__ __forceinline__ explicit MtIntBatch(Mt& r) : rng(r), cursor(0) {
+    rng.template next_batch<K>(words);
+  }
+  __device__ __forceinline__ uint32_t word() {
+    uint32_t v = 0;
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (k == cursor) {
+        v = words[k];
+        hit = true;
+      }
+    ++cursor;
+    return hit ? v : rng.next();
+  }
+  __device__ __forceinline__ int uniform_int(int a, int b) {
+    uint32_t range = (uint32_t)b - (uint32_t)a + 1u;
+    uint64_t product = (uint64_t)word() * (uint64_t)range;
+    uint32_t low = (uint32_t)product;
+    if (low < range) {
+      uint32_t threshold = (0u - range) % range;
+      while (low < threshold) {
+        product = (uint64_t)word() * (uint64_t)range;
         low = (uint32_t)product;
       }
     }
@@ -148,7 +244,7 @@ struct StepOut {
 template <class Env>
 __device__ __forceinline__ void env_step(const StateView& sv, int eid, int& flags,
                                          typename Env::State& s, typename Env::Act a,
-                                         bool force_reset, StepOut& so) {
+                                         bool force_reset, StepOut& so, int& mt_idx) {
   int done = flags & 1;
   int cur = flags >> 1;
   bool reset = force_reset || done;
@@ -156,18 +252,18 @@ __device__ __forceinline__ void env_step(const StateView& sv, int eid, int& flag
     cur = 0;
     done = 0;
     if (Env::kRngInReset) {
-      Mt rng(sv, eid);
+      Mt rng(sv, eid, mt_idx);
       Env::reset(sv, s, &rng, so);
-      rng.save(sv, eid);
+      mt_idx = rng.idx;
     } else {
       Env::reset(sv, s, nullptr, so);
     }
   } else {
     ++cur;
     if (Env::kRngInStep) {
-      Mt rng(sv, eid);
+      Mt rng(sv, eid, mt_idx);
       Env::step(sv, s, a, cur, done, &rng, so);
-      rng.save(sv, eid);
+      mt_idx = rng.idx;
     } else {
       Env::step(sv, s, a, cur, done, nullptr, so);
     }
@@ -187,15 +283,27 @@ step_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ acti
   so.reward = 0.f;
   so.extra = 0.f;
   int eid = 0, flags = 0;
+  typename Env::Act a = typename Env::Act();
   if (active) {
+    // inputs no earlier kernel of the stream writes: fetch them before the grid dependency
     eid = env_ids ? env_ids[row] : row;
-    typename Env::Act a = typename Env::Act();
     if (!force_reset) a = action[row];
+  }
+  // Programmatic dependent launch: let the next step's grid start launching now, and wait
+  // here for the previous step's grid (it owns the state and the output slab until done).
+  // Both are no-ops when the kernel is launched without the PDL attribute.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (active) {
+    constexpr bool kRng = Env::kRngInReset || Env::kRngInStep;
     flags = sv.flags[eid];
+    int mt_idx = kRng ? sv.mt_idx[eid] : 0;
+    const int mt_idx0 = mt_idx;
     Env::load(sv, eid, s);
-    env_step<Env>(sv, eid, flags, s, a, force_reset != 0, so);
+    env_step<Env>(sv, eid, flags, s, a, force_reset != 0, so, mt_idx);
     Env::store(sv, eid, s);
     sv.flags[eid] = flags;
+    if (kRng && mt_idx != mt_idx0) sv.mt_idx[eid] = mt_idx;
     write_common(ov, row, eid + sv.env_id_offset, flags >> 1, flags & 1, so.reward,
                  sv.max_steps);
   }
@@ -216,9 +324,11 @@ rollout_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ a
   const int n = sv.n_envs;
   bool active = eid < n;
   typename Env::State s;
-  int flags = 0;
+  int flags = 0, mt_idx = 0;
+  constexpr bool kRng = Env::kRngInReset || Env::kRngInStep;
   if (active) {
     flags = sv.flags[eid];
+    if (kRng) mt_idx = sv.mt_idx[eid];
     Env::load(sv, eid, s);
   }
   typename Env::Act a_next = typename Env::Act();
@@ -231,7 +341,7 @@ rollout_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ a
     typename Env::Act a = a_next;
     if (active && t + 1 < T) a_next = actions[(int64_t)(t + 1) * n + eid];  // prefetch
     if (active) {
-      env_step<Env>(sv, eid, flags, s, a, false, so);
+      env_step<Env>(sv, eid, flags, s, a, false, so, mt_idx);
       write_common(ov, row, eid + sv.env_id_offset, flags >> 1, flags & 1, so.reward,
                    sv.max_steps);
     }
@@ -245,6 +355,7 @@ rollout_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ a
   if (active) {
     Env::store(sv, eid, s);
     sv.flags[eid] = flags;
+    if (kRng) sv.mt_idx[eid] = mt_idx;
   }
 }
 
@@ -261,13 +372,30 @@ struct LaunchArgs {
 };
 typedef cudaError_t (*launch_fn)(const LaunchArgs&);
 
+// ENVPOOL_B200_PDL=0 turns the programmatic-dependent-launch attribute off (A/B switch).
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ENVPOOL_B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 template <class Env>
 cudaError_t launch_step(const LaunchArgs& a) {
-  int grid = (a.n + kBlock - 1) / kBlock;
-  step_kernel<Env><<<grid, kBlock, 0, a.stream>>>(
-      a.sv, a.ov, static_cast<const typename Env::Act*>(a.action), a.env_ids, a.n,
-      a.force_reset);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((a.n + kBlock - 1) / kBlock);
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, step_kernel<Env>, a.sv, a.ov,
+                            static_cast<const typename Env::Act*>(a.action), a.env_ids, a.n,
+                            a.force_reset);
 }
 template <class Env>
 cudaError_t launch_rollout(const LaunchArgs& a) {

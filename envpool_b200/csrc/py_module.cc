@@ -267,6 +267,9 @@ struct PoolHandle {
 struct SlabLease {  // keeps the pool alive and returns the pinned slab when numpy lets go
   std::shared_ptr<PoolHandle> pool;
   void* slab;
+  SlabLease(std::shared_ptr<PoolHandle> p, void* s) : pool(std::move(p)), slab(s) {}
+  SlabLease(const SlabLease&) = delete;
+  SlabLease& operator=(const SlabLease&) = delete;
   ~SlabLease() {
     if (pool && pool->p && slab) epb_release_slab(pool->p, slab);
   }
@@ -382,7 +385,7 @@ class PoolBase {
       rc = epb_recv_slab(h->p, &slab, &n);
     }
     check(rc);
-    auto lease = std::make_shared<SlabLease>(SlabLease{h, slab});
+    auto lease = std::make_shared<SlabLease>(h, slab);
     std::vector<py::array> ret;
     ret.reserve(keys.size());
     for (const epb_key_info& k : keys) {

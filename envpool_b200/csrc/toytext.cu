@@ -146,10 +146,11 @@ struct Taxi {
   static __device__ __forceinline__ void load(const StateView& sv, int e, State& s) { load_i1(sv, e, s); }
   static __device__ __forceinline__ void store(const StateView& sv, int e, const State& s) { store_i1(sv, e, s); }
   static __device__ __forceinline__ void reset(const StateView&, State& st, Mt* rng, StepOut& so) {
-    int x = rng->uniform_int(0, 4);
-    int y = rng->uniform_int(0, 4);
-    int s = rng->uniform_int(0, 3);
-    int t = rng->uniform_int(0, 3);
+    MtIntBatch<4> b(*rng);
+    int x = b.uniform_int(0, 4);
+    int y = b.uniform_int(0, 4);
+    int s = b.uniform_int(0, 3);
+    int t = b.uniform_int(0, 3);
     st.w = x | (y << 4) | (s << 8) | (t << 12);
     so.reward = 0.0f;
   }
@@ -340,16 +341,18 @@ struct Blackjack {
       return n == 2 && ((c0 == 1 && c1 == 10) || (c0 == 10 && c1 == 1));
     }
   };
-  static __device__ __forceinline__ int draw(Mt* rng) {  // DrawCard, blackjack.h:108
+  template <class Rng>
+  static __device__ __forceinline__ int draw(Rng* rng) {  // DrawCard, blackjack.h:108
     int c = rng->uniform_int(1, 13);
     return c < 10 ? c : 10;
   }
   static __device__ __forceinline__ void reset(const StateView&, State& s, Mt* rng, StepOut& so) {
     Hand p, d;
-    p.push(draw(rng));
-    p.push(draw(rng));
-    d.push(draw(rng));
-    d.push(draw(rng));
+    MtIntBatch<4> b(*rng);
+    p.push(draw(&b));
+    p.push(draw(&b));
+    d.push(draw(&b));
+    d.push(draw(&b));
     s.w0 = p.pack();
     s.w1 = d.pack();
     so.reward = 0.0f;

@@ -1,0 +1,109 @@
+"""Env-id sharding across the GPUs of one box (one process per GPU).
+
+The batched step path shards naturally: envs are independent (own mt19937, own state), so
+rank r of G owns the contiguous global ids [offset, offset + count) and seeds them with
+`seed + global_env_id` exactly as a single pool would (envpool/core/env.h:101-111) -- results
+do not depend on G.  The one exchange step of the path is an all-gather of the output
+columns, which reassembles the full `[num_envs, ...]` batch on every rank over NCCL /
+NVLink (gloo on CPU tensors in the host-logic tests).
+
+    pool = ShardedPool("CartPole-v1", num_envs=1 << 20)         # inside torchrun
+    out = pool.reset_device(); full = pool.all_gather()
+    out = pool.step_device(local_actions); full = pool.all_gather()
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+
+def shard_range(num_envs: int, rank: int, world: int) -> Tuple[int, int]:
+    """(global id of the first local env, number of local envs) for `rank` of `world`.
+    Contiguous blocks; the all-gather needs equal shards, so num_envs % world must be 0."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    if num_envs % world != 0:
+        raise ValueError(f"num_envs={num_envs} is not divisible by world_size={world}")
+    count = num_envs // world
+    return rank * count, count
+
+
+def all_gather_columns(local: Dict[str, "object"], full: Optional[Dict[str, "object"]] = None,
+                       group=None) -> Dict[str, "object"]:
+    """All-gather every column of `local` ({key: tensor [n_local, ...]}) into `full`
+    ({key: tensor [world * n_local, ...]}, allocated when None).  Rank r's rows land at
+    [r * n_local, (r + 1) * n_local): global env-id order."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    if full is None:
+        full = {k: torch.empty((world * v.shape[0],) + tuple(v.shape[1:]), dtype=v.dtype,
+                               device=v.device) for k, v in local.items()}
+    for k, v in local.items():
+        src = v if v.is_contiguous() else v.contiguous()
+        if src.dtype == torch.bool:  # gloo/nccl move bytes; bool is reinterpreted as uint8
+            dist.all_gather_into_tensor(full[k].view(torch.uint8), src.view(torch.uint8),
+                                        group=group)
+        else:
+            dist.all_gather_into_tensor(full[k], src, group=group)
+    return full
+
+
+class ShardedPool:
+    """This rank's shard of a `num_envs`-wide pool plus the all-gather of its outputs."""
+
+    def __init__(self, task_id: str, num_envs: int, seed: int = 42, group=None,
+                 device: Optional[int] = None, precision: str = "f64", **task_kwargs):
+        import torch
+        import torch.distributed as dist
+
+        from . import _capi
+        from .registration import registry
+        from . import _ensure_registered
+
+        _ensure_registered()
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.offset, self.count = shard_range(num_envs, self.rank, self.world)
+        self.num_envs = num_envs
+        if device is None:
+            device = torch.cuda.current_device()
+        _, spec_cls, kwargs = registry.specs[task_id]
+        kwargs = {**kwargs, **task_kwargs}
+        engine_task = spec_cls.replace("EnvSpec", "").replace("Gym", "")
+        iopt = -1
+        if engine_task == "FrozenLake":
+            iopt = kwargs.get("size", 4)
+        elif engine_task == "Pendulum":
+            iopt = kwargs.get("version", 0)
+        elif engine_task == "CliffWalking":
+            iopt = 1 if kwargs.get("is_slippery", False) else 0
+        elif engine_task == "Blackjack":
+            iopt = (1 if kwargs.get("natural", False) else 0) | (2 if kwargs.get("sab", True) else 0)
+        self.pool = _capi.CPool(engine_task, self.count, seed=seed,
+                                max_episode_steps=kwargs.get("max_episode_steps", -1),
+                                iopt=iopt, device=device, precision=precision,
+                                env_id_offset=self.offset)
+        self.stream = torch.cuda.ExternalStream(self.pool.stream, device=f"cuda:{device}")
+        self._full = None
+
+    def reset_device(self):
+        self.pool.reset_device()
+        return self.pool.outputs_torch()
+
+    def step_device(self, local_actions):
+        """`local_actions`: this rank's [count, ...] slice of the global action batch."""
+        self.pool.step_device(local_actions)
+        return self.pool.outputs_torch()
+
+    def all_gather(self):
+        """Full `[num_envs, ...]` batch of the last step on every rank (pool stream)."""
+        import torch
+
+        local = self.pool.outputs_torch()
+        if self.world == 1:
+            return local
+        with torch.cuda.stream(self.stream):
+            self._full = all_gather_columns(local, self._full, self.group)
+        return self._full

@@ -845,4 +845,19 @@ void epo_set_state(epo_pool* p, int eid, const double* s5, int done, int cur) {
   e->current_step = cur;
   e->elapsed = cur;
 }
+void epo_mjc_set(epo_pool* p, int eid, const double* s27, int done, int cur) {
+  epo_env* e = &p->envs[eid];
+  memcpy(mjc_qpos_mut(e->mj), s27, sizeof(double) * 9);
+  memcpy(mjc_qvel_mut(e->mj), s27 + 9, sizeof(double) * 9);
+  memcpy(mjc_warm_mut(e->mj), s27 + 18, sizeof(double) * 9);
+  e->done = done;
+  e->current_step = cur;
+  e->elapsed = cur;
+}
+void epo_mjc_get(const epo_pool* p, int eid, double* s27) {
+  const epo_env* e = &p->envs[eid];
+  memcpy(s27, mjc_qpos(e->mj), sizeof(double) * 9);
+  memcpy(s27 + 9, mjc_qvel(e->mj), sizeof(double) * 9);
+  memcpy(s27 + 18, mjc_warm_mut(e->mj), sizeof(double) * 9);
+}
 uint32_t epo_debug_draw(epo_pool* p, int eid) { return rng_next(&p->envs[eid].rng); }

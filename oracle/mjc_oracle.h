@@ -28,6 +28,7 @@ const double* mjc_qpos(const mjc_data* d);
 const double* mjc_qvel(const mjc_data* d);
 double* mjc_qpos_mut(mjc_data* d);
 double* mjc_qvel_mut(mjc_data* d);
+double* mjc_warm_mut(mjc_data* d); /* qacc_warmstart */
 /* mj_forward on the current qpos/qvel (used by tests to set a state) */
 void mjc_forward(const mjc_model* m, mjc_data* d);
 /* number of active constraint rows after the last forward/step (diagnostics) */

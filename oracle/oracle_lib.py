@@ -56,6 +56,8 @@ def lib():
         L.epo_action_row_elems.argtypes = [vp]
         L.epo_get_state.argtypes = [vp, ci, vp, vp, vp]
         L.epo_set_state.argtypes = [vp, ci, vp, ci, ci]
+        L.epo_mjc_set.argtypes = [vp, ci, vp, ci, ci]
+        L.epo_mjc_get.argtypes = [vp, ci, vp]
         L.epo_debug_draw.restype = ctypes.c_uint32
         L.epo_debug_draw.argtypes = [vp, ci]
         _lib = L
@@ -150,5 +152,74 @@ class OraclePool:
         lib().epo_get_state(self.h, eid, buf, ctypes.byref(d), ctypes.byref(c))
         return list(buf), d.value, c.value
 
+    def mjc_set(self, eid, s27, done, cur):
+        buf = np.ascontiguousarray(s27, dtype=np.float64)
+        lib().epo_mjc_set(self.h, eid, buf.ctypes.data, int(done), int(cur))
+
+    def mjc_get(self, eid):
+        buf = np.zeros(27)
+        lib().epo_mjc_get(self.h, eid, buf.ctypes.data)
+        return buf
+
     def draw(self, eid):
         return lib().epo_debug_draw(self.h, eid)
+
+
+class MjcSim:
+    """Direct handle on the HalfCheetah physics restatement (oracle/mjc_oracle.c)."""
+
+    def __init__(self):
+        L = lib()
+        vp = ctypes.c_void_p
+        L.mjc_make_half_cheetah.restype = vp
+        L.mjc_make_data.restype = vp
+        L.mjc_make_data.argtypes = [vp]
+        L.mjc_free_model.argtypes = [vp]
+        L.mjc_free_data.argtypes = [vp]
+        L.mjc_qpos_mut.restype = ctypes.POINTER(ctypes.c_double)
+        L.mjc_qpos_mut.argtypes = [vp]
+        L.mjc_qvel_mut.restype = ctypes.POINTER(ctypes.c_double)
+        L.mjc_qvel_mut.argtypes = [vp]
+        L.mjc_step.argtypes = [vp, vp, vp, ctypes.c_int]
+        L.mjc_forward.argtypes = [vp, vp]
+        L.mjc_nefc.argtypes = [vp]
+        L.mjc_model_constants.argtypes = [vp, vp, ctypes.c_int]
+        self.L = L
+        self.m = L.mjc_make_half_cheetah()
+        self.d = L.mjc_make_data(self.m)
+
+    def close(self):
+        if self.d:
+            self.L.mjc_free_data(self.d)
+            self.L.mjc_free_model(self.m)
+            self.d = self.m = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def qpos(self):
+        return np.ctypeslib.as_array(self.L.mjc_qpos_mut(self.d), shape=(9,))
+
+    @property
+    def qvel(self):
+        return np.ctypeslib.as_array(self.L.mjc_qvel_mut(self.d), shape=(9,))
+
+    def step(self, action, frame_skip=1):
+        a = np.ascontiguousarray(action, dtype=np.float64)
+        self.L.mjc_step(self.m, self.d, a.ctypes.data, frame_skip)
+
+    def forward(self):
+        self.L.mjc_forward(self.m, self.d)
+
+    @property
+    def nefc(self):
+        return self.L.mjc_nefc(self.d)
+
+    def constants(self):
+        buf = np.zeros(64)
+        n = self.L.mjc_model_constants(self.m, buf.ctypes.data, 64)
+        c = buf[:n]
+        return {"mass": c[0:28:4].copy(), "com": np.stack([c[1:28:4], c[2:28:4]], 1),
+                "iyy": c[3:28:4].copy(), "dof_invweight0": c[28:37].copy(),
+                "body_invweight0": c[37:51].reshape(7, 2).copy(), "meaninertia": c[51]}
