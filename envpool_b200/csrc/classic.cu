@@ -19,10 +19,13 @@ template <typename R> struct M;
 template <> struct M<double> {
   static __device__ __forceinline__ double sin_(double x) { return sin(x); }
   static __device__ __forceinline__ double cos_(double x) { return cos(x); }
+  // one argument reduction for both; same values as sin(x), cos(x)
+  static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
 };
 template <> struct M<float> {
   static __device__ __forceinline__ float sin_(float x) { return sinf(x); }
   static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
+  static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
 };
 
 template <typename R, int NR>
@@ -73,7 +76,8 @@ struct CartPole {
     R x = s.v[0], x_dot = s.v[1], theta = s.v[2], theta_dot = s.v[3];
     done = (cur >= sv.max_steps);
     R force = act == 1 ? kForceMag : -kForceMag;
-    R costheta = M<R>::cos_(theta), sintheta = M<R>::sin_(theta);
+    R costheta, sintheta;
+    M<R>::sincos_(theta, &sintheta, &costheta);
     R temp = (force + kMassPoleLength * theta_dot * theta_dot * sintheta) / kMassTotal;
     R theta_acc = (kGravity * sintheta - costheta * temp) /
                   (kLength * ((R)(4.0 / 3.0) - kMassPole * costheta * costheta / kMassTotal));
@@ -153,8 +157,10 @@ struct Pendulum {
                                                    const State& s, const StepOut&) {
     if (!ov.env[0]) return;
     float* o = static_cast<float*>(ov.env[0]) + row * 3;
-    o[0] = (float)M<R>::cos_(s.v[0]);
-    o[1] = (float)M<R>::sin_(s.v[0]);
+    R sn, cs;
+    M<R>::sincos_(s.v[0], &sn, &cs);
+    o[0] = (float)cs;
+    o[1] = (float)sn;
     o[2] = (float)s.v[1];
   }
 };
@@ -177,7 +183,8 @@ struct Acrobot {
     const R kG = (R)9.8, kL = 1, kM = 1, kLC = (R)0.5, kI = 1;
     const R kHalfPi = (R)(M_PI / 2);
     R theta1 = s.s0, theta2 = s.s1, dtheta1 = s.s2, dtheta2 = s.s3, a = s.s4;
-    R c2 = M<R>::cos_(theta2), s2 = M<R>::sin_(theta2);
+    R c2, s2;
+    M<R>::sincos_(theta2, &s2, &c2);
     R d1 = kM * kLC * kLC + kM * (kL * kL + kLC * kLC + 2 * kL * kLC * c2) + kI * 2;
     R d2 = kM * (kLC * kLC + kL * kLC * c2) + kI;
     R phi2 = kM * kLC * kG * M<R>::cos_(theta1 + theta2 - kHalfPi);
@@ -237,8 +244,11 @@ struct Acrobot {
                                                    const State& s, const StepOut&) {
     if (ov.env[0]) {
       float2* o = reinterpret_cast<float2*>(static_cast<float*>(ov.env[0]) + row * 6);
-      o[0] = make_float2((float)M<R>::cos_(s.v[0]), (float)M<R>::sin_(s.v[0]));
-      o[1] = make_float2((float)M<R>::cos_(s.v[1]), (float)M<R>::sin_(s.v[1]));
+      R s0, c0, s1, c1;
+      M<R>::sincos_(s.v[0], &s0, &c0);
+      M<R>::sincos_(s.v[1], &s1, &c1);
+      o[0] = make_float2((float)c0, (float)s0);
+      o[1] = make_float2((float)c1, (float)s1);
       o[2] = make_float2((float)s.v[2], (float)s.v[3]);
     }
     if (ov.env[1]) {

@@ -49,77 +49,97 @@ struct OutView {
 };
 
 // ---------------------------------------------------------------------------------------
-// std::mt19937 on the device.  The table lives in HBM as mt[k*N + env] so that envs that
-// are in lockstep read/write coalesced rows.  Words are regenerated one at a time (the
-// block "twist" of the textbook implementation unrolled in time -- identical sequence,
-// 12 B read + 4 B written per draw instead of a 2.5 KB burst).
+// std::mt19937 on the device.
+//
+// Layout: the 624-word table of env e is cut into 78 chunks of 8 words; chunk c of env e is
+// the 32-byte sector at word offset (c*N + e)*8.  One DRAM sector therefore holds 8
+// consecutive words of ONE env (envs draw at different times, so a warp's lanes sit at
+// different positions of their tables; with a word-major layout every 4-byte access would
+// cost a whole sector), while lanes that do move in lockstep still touch adjacent sectors.
+//
+// Regeneration: the textbook "twist" regenerates all 624 words at once; here a chunk of 8 is
+// regenerated when the read position enters it.  Word i needs the current words i, i+1 and
+// i+397; inside a chunk-sized batch none of those has been regenerated earlier in the batch
+// except i+1's predecessor, whose *old* value is what the recurrence wants, so the batch is
+// 4 sector reads (own chunk, first word of the next, the two chunks holding i+397..i+404)
+// + 1 sector write per 8 draws, all loads in flight together.  The sequence is identical to
+// std::mt19937's.
 struct Mt {
-  uint32_t* base;  // &mt[eid]
-  int64_t stride;  // N
-  int idx;
-  __device__ __forceinline__ Mt(const StateView& sv, int eid)
-      : base(sv.mt + eid), stride(sv.n_envs), idx(sv.mt_idx[eid]) {}
+  uint32_t* tab;   // sv.mt
+  int64_t n;       // N
+  int eid;
+  int idx;         // next word to hand out, 0..623
+  uint32_t cw[8];  // register copy of the chunk idx lies in (raw words)
+  bool have;
+  __device__ __forceinline__ Mt(const StateView& sv, int eid_)
+      : tab(sv.mt), n(sv.n_envs), eid(eid_), idx(sv.mt_idx[eid_]), have(false) {}
   // idx already loaded by the caller (issued together with the env-state loads so the
   // draw does not pay a second dependent round trip)
-  __device__ __forceinline__ Mt(const StateView& sv, int eid, int idx_)
-      : base(sv.mt + eid), stride(sv.n_envs), idx(idx_) {}
-  __device__ __forceinline__ uint32_t next() {
-    int i = idx;
-    int i1 = (i + 1 == kMtN) ? 0 : i + 1;
-    int im = (i + kMtM >= kMtN) ? i + kMtM - kMtN : i + kMtM;
-    uint32_t a = base[(int64_t)i * stride];
-    uint32_t b = base[(int64_t)i1 * stride];
-    uint32_t c = base[(int64_t)im * stride];
+  __device__ __forceinline__ Mt(const StateView& sv, int eid_, int idx_)
+      : tab(sv.mt), n(sv.n_envs), eid(eid_), idx(idx_), have(false) {}
+  __device__ __forceinline__ void save(const StateView& sv, int e) { sv.mt_idx[e] = idx; }
+
+  __device__ __forceinline__ uint4* sector(int chunk) const {
+    return reinterpret_cast<uint4*>(tab + ((int64_t)chunk * n + eid) * 8);
+  }
+  static __device__ __forceinline__ uint32_t twist(uint32_t a, uint32_t b, uint32_t m) {
     uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-    uint32_t v = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-    base[(int64_t)i * stride] = v;
-    idx = i1;
+    return m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+  }
+  static __device__ __forceinline__ uint32_t temper(uint32_t v) {
     v ^= (v >> 11);
     v ^= (v << 7) & 0x9d2c5680u;
     v ^= (v << 15) & 0xefc60000u;
     v ^= (v >> 18);
     return v;
   }
-  __device__ __forceinline__ void save(const StateView& sv, int eid) { sv.mt_idx[eid] = idx; }
-
-  // K consecutive draws in ONE memory round trip.  Regenerating word i needs the current
-  // words i, i+1 and i+397; for K <= 226 none of those is itself regenerated earlier in the
-  // same batch except word i+1, whose *old* value is what the recurrence wants -- so all
-  // 2K+1 loads can be issued together (memory-level parallelism instead of K dependent
-  // DRAM latencies), then the K new words are stored.  Same sequence as K next() calls.
+  // regenerate chunk c in place; cw <- its new raw words
+  __device__ __forceinline__ void regen(int c) {
+    int c1 = c + 1, c49 = c + 49, c50 = c + 50;
+    c1 = c1 >= 78 ? c1 - 78 : c1;
+    c49 = c49 >= 78 ? c49 - 78 : c49;
+    c50 = c50 >= 78 ? c50 - 78 : c50;
+    uint4* own = sector(c);
+    const uint4 o0 = own[0], o1 = own[1];
+    const uint32_t nx = reinterpret_cast<const uint32_t*>(sector(c1))[0];
+    const uint4 m0 = sector(c49)[1];                       // words 4..7 of chunk c+49
+    const uint4 m1 = sector(c50)[0];                       // words 0..3 of chunk c+50
+    const uint32_t m2 = reinterpret_cast<const uint32_t*>(sector(c50))[4];  // word 4
+    // word i+397 for i = 8c+k, k = 0..7: chunk c+49 words 5,6,7 then chunk c+50 words 0..4
+    cw[0] = twist(o0.x, o0.y, m0.y);
+    cw[1] = twist(o0.y, o0.z, m0.z);
+    cw[2] = twist(o0.z, o0.w, m0.w);
+    cw[3] = twist(o0.w, o1.x, m1.x);
+    cw[4] = twist(o1.x, o1.y, m1.y);
+    cw[5] = twist(o1.y, o1.z, m1.z);
+    cw[6] = twist(o1.z, o1.w, m1.w);
+    cw[7] = twist(o1.w, nx, m2);
+    own[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+    own[1] = make_uint4(cw[4], cw[5], cw[6], cw[7]);
+    have = true;
+  }
+  __device__ __forceinline__ uint32_t next() {
+    const int k = idx & 7;
+    if (k == 0) {
+      regen(idx >> 3);
+    } else if (!have) {
+      const uint4* own = sector(idx >> 3);
+      const uint4 o0 = own[0], o1 = own[1];
+      cw[0] = o0.x; cw[1] = o0.y; cw[2] = o0.z; cw[3] = o0.w;
+      cw[4] = o1.x; cw[5] = o1.y; cw[6] = o1.z; cw[7] = o1.w;
+      have = true;
+    }
+    uint32_t v = cw[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) v = (k == j) ? cw[j] : v;
+    idx = (idx + 1 == kMtN) ? 0 : idx + 1;
+    return temper(v);
+  }
+  // K consecutive draws (same sequence as K next() calls)
   template <int K>
   __device__ __forceinline__ void next_batch(uint32_t (&out)[K]) {
-    static_assert(K >= 1 && K <= 64, "batch too large");
-    uint32_t w[K + 1], m[K];
-    const int i = idx;
 #pragma unroll
-    for (int k = 0; k <= K; ++k) {
-      int j = i + k;
-      j = j >= kMtN ? j - kMtN : j;
-      w[k] = base[(int64_t)j * stride];
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      int j = i + k + kMtM;
-      j = j >= kMtN ? j - kMtN : j;
-      j = j >= kMtN ? j - kMtN : j;
-      m[k] = base[(int64_t)j * stride];
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      uint32_t y = (w[k] & 0x80000000u) | (w[k + 1] & 0x7fffffffu);
-      uint32_t v = m[k] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      int j = i + k;
-      j = j >= kMtN ? j - kMtN : j;
-      base[(int64_t)j * stride] = v;
-      v ^= (v >> 11);
-      v ^= (v << 7) & 0x9d2c5680u;
-      v ^= (v << 15) & 0xefc60000u;
-      v ^= (v >> 18);
-      out[k] = v;
-    }
-    int j = i + K;
-    idx = j >= kMtN ? j - kMtN : j;
+    for (int k = 0; k < K; ++k) out[k] = next();
   }
 
   // std::generate_canonical<double,53> (libstdc++ 13 bits/random.tcc:3349-3381) from two
@@ -392,7 +412,12 @@ cudaError_t launch_step(const LaunchArgs& a) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  // PDL pays off for direct launches (hides ~0.7 us of launch latency per step); inside a
+  // captured graph the programmatic edges measured slower than plain kernel->kernel edges
+  // (5.9 vs 5.0 us/step, CartPole N=65536), so captures keep full serialisation.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(a.stream, &cap);
+  cfg.numAttrs = (pdl_enabled() && cap == cudaStreamCaptureStatusNone) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, step_kernel<Env>, a.sv, a.ov,
                             static_cast<const typename Env::Act*>(a.action), a.env_ids, a.n,
                             a.force_reset);

@@ -21,7 +21,9 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 
 namespace epb {
 
@@ -593,6 +595,8 @@ __device__ void hc_substep(WarpMem& w, int lane) {
       q1 = warp_sum(q1);
       q2 = warp_sum(q2);
       __syncwarp();
+      double sn2 = (lane < NV) ? w.srch[lane] * w.srch[lane] : 0.0;
+      const double gtol = cm.tolerance * 0.01 * sqrt(warp_sum(sn2)) / scale;
       double lo = 0, hi = INFINITY, alpha = 0;
       for (int k = 0; k < cm.ls_iter; ++k) {
         double d1 = 0, d2 = 0;
@@ -605,7 +609,7 @@ __device__ void hc_substep(WarpMem& w, int lane) {
         }
         d1 = warp_sum(d1) + (q1 + alpha * q2);
         d2 = warp_sum(d2) + q2;
-        if (fabs(d1) < 1e-14 * (1 + fabs(q1))) break;
+        if (fabs(d1) < gtol) break;
         if (d1 < 0) lo = alpha; else hi = alpha;
         double next = alpha - d1 / d2;
         if (!(next > lo && next < hi)) next = isinf(hi) ? 2 * alpha + 1 : 0.5 * (lo + hi);
@@ -668,12 +672,13 @@ hc_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict__ act
   if (row >= n) return;  // whole warp exits together
   WarpMem& w = wm[wid];
   const int eid = env_ids ? env_ids[row] : row;
-  double* st = static_cast<double*>(sv.rstate) + (int64_t)eid * kStateReals;
+  double* st = static_cast<double*>(sv.rstate) + eid;  // SoA: real k of env e at k*N + e
+  const int64_t N = sv.n_envs;
   int flags = sv.flags[eid];
   if (lane < NV) {
-    w.q[lane] = st[lane];
-    w.v[lane] = st[NV + lane];
-    w.warm[lane] = st[2 * NV + lane];
+    w.q[lane] = st[lane * N];
+    w.v[lane] = st[(NV + lane) * N];
+    w.warm[lane] = st[(2 * NV + lane) * N];
   }
   __syncwarp();
   for (int t = 0; t < T; ++t) {
@@ -689,8 +694,8 @@ hc_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict__ act
       done = 0;
       if (lane == 0) {
         Mt rng(sv, eid);
-        double saved = st[27];
-        bool has = st[28] != 0.0;
+        double saved = st[27 * N];
+        bool has = st[28 * N] != 0.0;
         double u[NV];
         rng.uniform_real_batch<NV>(-prm.reset_noise_scale, prm.reset_noise_scale, u);
         for (int i = 0; i < NV; ++i) w.q[i] = 0.0 + u[i];
@@ -698,8 +703,8 @@ hc_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict__ act
           w.v[i] = 0.0 + hc_normal(rng, saved, has, 0.0, prm.reset_noise_scale);
         for (int i = 0; i < NV; ++i) w.warm[i] = 0.0;
         rng.save(sv, eid);
-        st[27] = saved;
-        st[28] = has ? 1.0 : 0.0;
+        st[27 * N] = saved;
+        st[28 * N] = has ? 1.0 : 0.0;
       }
       __syncwarp();
     } else {
@@ -730,11 +735,100 @@ hc_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict__ act
     __syncwarp();
   }
   if (lane < NV) {
-    st[lane] = w.q[lane];
-    st[NV + lane] = w.v[lane];
-    st[2 * NV + lane] = w.warm[lane];
+    st[lane * N] = w.q[lane];
+    st[(NV + lane) * N] = w.v[lane];
+    st[(2 * NV + lane) * N] = w.warm[lane];
   }
   if (lane == 0) sv.flags[eid] = flags;
+}
+
+}  // namespace
+}  // namespace epb
+
+#include "mujoco_thread.cuh"
+
+namespace epb {
+namespace {
+
+constexpr int kThreadBlock = 64;
+
+// One launch = T sync steps of `n` batch rows; ONE THREAD PER ENV (row).
+__global__ void __launch_bounds__(kThreadBlock)
+hc_thread_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict__ action,
+                 const int32_t* __restrict__ env_ids, int n, int force_reset, int T) {
+  const int row = blockIdx.x * kThreadBlock + threadIdx.x;
+  if (row >= n) return;
+  const int eid = env_ids ? env_ids[row] : row;
+  const int64_t N = sv.n_envs;
+  double* st = static_cast<double*>(sv.rstate) + eid;
+  hct::HcState s;
+  hct::Rows e;
+  int flags = sv.flags[eid];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    s.q[i] = st[i * N];
+    s.v[i] = st[(NV + i) * N];
+    s.warm[i] = st[(2 * NV + i) * N];
+  }
+  for (int t = 0; t < T; ++t) {
+    const int64_t orow = (int64_t)t * ov.t_stride_rows + row;
+    int done = flags & 1, cur = flags >> 1;
+    const bool reset = force_reset || done;
+    double xv = 0, ctrl_cost = 0, x_after = 0;
+    float reward = 0.0f;
+    if (reset) {
+      cur = 0;
+      done = 0;
+      Mt rng(sv, eid);
+      double saved = st[27 * N];
+      bool has = st[28 * N] != 0.0;
+      double u[NV];
+      rng.uniform_real_batch<NV>(-prm.reset_noise_scale, prm.reset_noise_scale, u);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s.q[i] = 0.0 + u[i];
+      for (int i = 0; i < NV; ++i)
+        s.v[i] = 0.0 + hc_normal(rng, saved, has, 0.0, prm.reset_noise_scale);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s.warm[i] = 0.0;
+      rng.save(sv, eid);
+      st[27 * N] = saved;
+      st[28 * N] = has ? 1.0 : 0.0;
+    } else {
+      ++cur;
+      const double* act = action + ((int64_t)t * n + row) * NU;
+#pragma unroll
+      for (int k = 0; k < NU; ++k) s.ctrl[k] = act[k];
+      const double x_before = s.q[0];
+      for (int k = 0; k < prm.frame_skip; ++k) hct::substep(s, e);
+      x_after = s.q[0];
+#pragma unroll
+      for (int k = 0; k < NU; ++k) ctrl_cost += prm.ctrl_cost_weight * s.ctrl[k] * s.ctrl[k];
+      const double dt = prm.frame_skip * cm.timestep;
+      xv = (x_after - x_before) / dt;
+      reward = (float)(xv * prm.forward_reward_weight - ctrl_cost);
+      done = (cur >= sv.max_steps);
+    }
+    flags = (cur << 1) | done;
+    write_common(ov, orow, eid + sv.env_id_offset, cur, done, reward, sv.max_steps);
+    if (ov.env[1]) static_cast<double*>(ov.env[1])[orow] = xv * prm.forward_reward_weight;
+    if (ov.env[2]) static_cast<double*>(ov.env[2])[orow] = -ctrl_cost;
+    if (ov.env[3]) static_cast<double*>(ov.env[3])[orow] = x_after;
+    if (ov.env[4]) static_cast<double*>(ov.env[4])[orow] = xv;
+    if (ov.env[0]) {
+      double* o = static_cast<double*>(ov.env[0]) + orow * 17;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = s.q[k + 1];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) o[8 + k] = s.v[k];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    st[i * N] = s.q[i];
+    st[(NV + i) * N] = s.v[i];
+    st[(2 * NV + i) * N] = s.warm[i];
+  }
+  sv.flags[eid] = flags;
 }
 
 }  // namespace
@@ -742,6 +836,7 @@ hc_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict__ act
 struct MjcPool {
   HcParams prm;
   int num_envs;
+  bool warp_variant;  // ENVPOOL_B200_HC_KERNEL=warp selects the warp-per-env kernel
 };
 
 MjcPool* mjc_pool_create(int num_envs, int precision, int frame_skip, double ctrl_cost_weight,
@@ -756,6 +851,8 @@ MjcPool* mjc_pool_create(int num_envs, int precision, int frame_skip, double ctr
   m->prm.ctrl_cost_weight = ctrl_cost_weight;
   m->prm.forward_reward_weight = forward_reward_weight;
   m->prm.reset_noise_scale = reset_noise_scale;
+  const char* v = getenv("ENVPOOL_B200_HC_KERNEL");
+  m->warp_variant = v && std::string(v) == "warp";
   return m;
 }
 void mjc_pool_destroy(MjcPool* m) { delete m; }
@@ -764,16 +861,28 @@ int mjc_state_reals(const MjcPool*) { return kStateReals; }
 cudaError_t mjc_launch_step(MjcPool* m, const StateView& sv, const OutView& ov,
                             const double* d_action, const int32_t* d_env_ids, int n,
                             int force_reset, cudaStream_t stream) {
-  int grid = (n + kWarps - 1) / kWarps;
-  hc_kernel<<<grid, kWarps * 32, 0, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
-                                              force_reset, 1);
+  if (m->warp_variant) {
+    int grid = (n + kWarps - 1) / kWarps;
+    hc_kernel<<<grid, kWarps * 32, 0, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
+                                                force_reset, 1);
+  } else {
+    int grid = (n + kThreadBlock - 1) / kThreadBlock;
+    hc_thread_kernel<<<grid, kThreadBlock, 0, stream>>>(sv, ov, m->prm, d_action, d_env_ids,
+                                                        n, force_reset, 1);
+  }
   return cudaGetLastError();
 }
 cudaError_t mjc_launch_rollout(MjcPool* m, const StateView& sv, const OutView& ov,
                                const double* d_actions, int T, cudaStream_t stream) {
   int n = sv.n_envs;
-  int grid = (n + kWarps - 1) / kWarps;
-  hc_kernel<<<grid, kWarps * 32, 0, stream>>>(sv, ov, m->prm, d_actions, nullptr, n, 0, T);
+  if (m->warp_variant) {
+    int grid = (n + kWarps - 1) / kWarps;
+    hc_kernel<<<grid, kWarps * 32, 0, stream>>>(sv, ov, m->prm, d_actions, nullptr, n, 0, T);
+  } else {
+    int grid = (n + kThreadBlock - 1) / kThreadBlock;
+    hc_thread_kernel<<<grid, kThreadBlock, 0, stream>>>(sv, ov, m->prm, d_actions, nullptr, n,
+                                                        0, T);
+  }
   return cudaGetLastError();
 }
 

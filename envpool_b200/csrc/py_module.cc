@@ -379,10 +379,10 @@ class PoolBase {
   // a capsule keeps the slab (and the pool) alive until every returned array is dropped.
   std::vector<py::array> Recv() {
     void* slab = nullptr;
-    int n = 0, rc;
+    int n = 0, row0 = 0, rc;
     {
       py::gil_scoped_release release;
-      rc = epb_recv_slab(h->p, &slab, &n);
+      rc = epb_recv_slab_ex(h->p, &slab, &row0, &n);
     }
     check(rc);
     auto lease = std::make_shared<SlabLease>(h, slab);
@@ -393,7 +393,8 @@ class PoolBase {
       py::capsule cap(holder, [](void* p) { delete static_cast<std::shared_ptr<SlabLease>*>(p); });
       std::vector<py::ssize_t> shape = {n};
       for (int i = 0; i < k.ndim; ++i) shape.push_back(k.shape[i]);
-      char* base = static_cast<char*>(slab) + k.slab_offset;
+      char* base = static_cast<char*>(slab) + k.slab_offset +
+                   static_cast<size_t>(row0) * k.row_bytes;
       switch (k.dtype) {
         case EPB_I32: ret.emplace_back(py::array(shape, reinterpret_cast<int*>(base), cap)); break;
         case EPB_F32: ret.emplace_back(py::array(shape, reinterpret_cast<float*>(base), cap)); break;

@@ -20,8 +20,18 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) {
 }
 
 // --------------------------------------------------------------------------- FrozenLake
-// frozen_lake.h:58-108.  State: x | y<<8.  Maps (frozen_lake.h:63-69) as hole/goal bit masks
-// indexed by x*size+y.
+// frozen_lake.h:58-108.  Maps (frozen_lake.h:63-69) as hole/goal bit masks indexed by
+// x*size+y.
+//
+// State word: x | y<<3 | slip-queue<<6.  The env draws one uniform_int(-1,1) per step and
+// nothing at reset, so its mt19937 words are consumed strictly in order; instead of touching
+// the table every step (one 32-B sector for 4 useful bytes), a whole chunk of 8 words is
+// regenerated at once (4 sector reads + 1 write, common.cuh Mt::regen) and the 8 resulting
+// draws are queued in the state word as 2-bit codes under a marker bit: 0..2 = Lemire result
+// (uniform_int_dist.h:252-282 with range 3: product>>32), 3 = that word was REJECTED by
+// Lemire's test (low < 2^32 mod 3 = 1, i.e. the word is 0) and the next word decides.  Same
+// draws, same order, same results as drawing lazily -- RNG traffic drops from 32 to ~20 B per
+// step and 7 of 8 steps touch no RNG memory at all.
 struct FrozenLake {
   using Act = int32_t;
   using State = IntState1;
@@ -29,8 +39,26 @@ struct FrozenLake {
   static __device__ __forceinline__ void load(const StateView& sv, int e, State& s) { load_i1(sv, e, s); }
   static __device__ __forceinline__ void store(const StateView& sv, int e, const State& s) { store_i1(sv, e, s); }
   static __device__ __forceinline__ void reset(const StateView&, State& s, Mt*, StepOut& so) {
-    s.w = 0;
+    s.w &= ~63;  // x = y = 0; the slip queue survives the episode boundary
+    if ((s.w >> 6) == 0) s.w |= 1 << 6;  // empty queue = marker bit only
     so.reward = 0.0f;
+  }
+  static __device__ __forceinline__ int pop_slip(uint32_t& queue, Mt* rng) {
+    for (;;) {
+      if (queue <= 1u) {  // empty: draw the next 8 engine words in one go
+        uint32_t w[8];
+        rng->next_batch<8>(w);
+        queue = 1u;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+          uint32_t code = w[k] == 0u ? 3u : (uint32_t)(((uint64_t)w[k] * 3ull) >> 32);
+          queue = (queue << 2) | code;
+        }
+      }
+      uint32_t code = queue & 3u;
+      queue >>= 2;
+      if (code != 3u) return (int)code - 1;
+    }
   }
   static __device__ __forceinline__ void step(const StateView& sv, State& s, Act act, int cur,
                                               int& done, Mt* rng, StepOut& so) {
@@ -43,9 +71,10 @@ struct FrozenLake {
                             (1ull << 54) | (1ull << 59);
     const uint64_t kGoal8 = 1ull << 63;
     const int size = sv.iopt;
-    int x = s.w & 0xff, y = (s.w >> 8) & 0xff;
+    int x = s.w & 7, y = (s.w >> 3) & 7;
+    uint32_t queue = (uint32_t)s.w >> 6;
     done = (cur >= sv.max_steps);
-    act = (act + rng->uniform_int(-1, 1) + 4) % 4;
+    act = (act + pop_slip(queue, rng) + 4) % 4;
     if (act == 0) {
       --y;
     } else if (act == 1) {
@@ -64,14 +93,14 @@ struct FrozenLake {
       done = 1;
       reward = ((goal >> cell) & 1ull) ? 1.0f : 0.0f;
     }
-    s.w = x | (y << 8);
+    s.w = (int32_t)((uint32_t)x | ((uint32_t)y << 3) | (queue << 6));
     so.reward = reward;
   }
   static __device__ __forceinline__ void write_obs(const StateView& sv, const OutView& ov,
                                                    int64_t row,
                                                    const State& s, const StepOut&) {
     if (!ov.env[0]) return;
-    int x = s.w & 0xff, y = (s.w >> 8) & 0xff;
+    int x = s.w & 7, y = (s.w >> 3) & 7;
     static_cast<int32_t*>(ov.env[0])[row] = x * sv.iopt + y;
   }
 };

@@ -49,6 +49,38 @@ def all_gather_columns(local: Dict[str, "object"], full: Optional[Dict[str, "obj
     return full
 
 
+def all_gather_packed(local_slab, full_slab=None, group=None):
+    """ONE collective for the whole step: all-gather the packed output slab (every column of
+    this rank, `slab_bytes` uint8) into `[world, slab_bytes]`.  Column k of rank r then sits
+    at `full[r, off_k : off_k + n_local*row_bytes]`; `packed_views` exposes it as a
+    `[world, n_local, ...]` tensor (global env-id order along the first two dims)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    if full_slab is None:
+        full_slab = torch.empty((world, local_slab.numel()), dtype=torch.uint8,
+                                device=local_slab.device)
+    dist.all_gather_into_tensor(full_slab, local_slab, group=group)
+    return full_slab
+
+
+def packed_views(full_slab, keys, n_local):
+    """{key: [world, n_local, ...] strided view} into a gathered slab (zero-copy)."""
+    import numpy as np
+    import torch
+
+    tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.float32): torch.float32,
+           np.dtype(np.float64): torch.float64, np.dtype(np.bool_): torch.bool}
+    out = {}
+    world = full_slab.shape[0]
+    for k in keys:
+        nb = k.row_bytes * n_local
+        col = full_slab[:, k.offset:k.offset + nb]                 # [world, nb] uint8
+        out[k.name] = col.view(tdt[k.dtype]).view((world, n_local) + tuple(k.shape))
+    return out
+
+
 class ShardedPool:
     """This rank's shard of a `num_envs`-wide pool plus the all-gather of its outputs."""
 
@@ -97,13 +129,24 @@ class ShardedPool:
         self.pool.step_device(local_actions)
         return self.pool.outputs_torch()
 
-    def all_gather(self):
-        """Full `[num_envs, ...]` batch of the last step on every rank (pool stream)."""
+    def all_gather(self, packed: bool = True):
+        """The full batch of the last step on every rank (enqueued on the pool stream).
+        packed=True: ONE all-gather of the packed slab, columns returned as
+        `[world, n_local, ...]` views; packed=False: one all-gather per column into
+        contiguous `[num_envs, ...]` tensors."""
         import torch
+
+        from ._capi import _torch_view
 
         local = self.pool.outputs_torch()
         if self.world == 1:
             return local
         with torch.cuda.stream(self.stream):
-            self._full = all_gather_columns(local, self._full, self.group)
-        return self._full
+            if not packed:
+                self._full = all_gather_columns(local, self._full, self.group)
+                return self._full
+            slab = _torch_view(self.pool.outputs_device_ptr(), (self.pool.slab_bytes,),
+                               torch.uint8, self.pool.device)
+            self._full_slab = all_gather_packed(slab, getattr(self, "_full_slab", None),
+                                                self.group)
+        return packed_views(self._full_slab, self.pool.keys, self.count)

@@ -557,6 +557,11 @@ static void solve_newton(const mjc_model* m, const efc_t* e, const double* M,
       q1 += search[i] * (Ma[i] - qfrc_smooth[i]);
       q2 += search[i] * Mv[i];
     }
+    /* stop when |phi'(alpha)| < tolerance * ls_tolerance * |search| / scale (MuJoCo's
+     * scaled gradient tolerance for the 1-D problem; ls_tolerance = 0.01) */
+    double snorm = 0;
+    for (int i = 0; i < NV; ++i) snorm += search[i] * search[i];
+    const double gtol = m->tolerance * 0.01 * sqrt(snorm) / scale;
     double lo = 0, hi = INFINITY, alpha = 0;
     for (int k = 0; k < m->ls_iter; ++k) {
       double d1 = q1 + alpha * q2, d2 = q2;
@@ -567,7 +572,7 @@ static void solve_newton(const mjc_model* m, const efc_t* e, const double* M,
           d2 += e->D[r] * Jv[r] * Jv[r];
         }
       }
-      if (fabs(d1) < 1e-14 * (1 + fabs(q1))) break;
+      if (fabs(d1) < gtol) break;
       if (d1 < 0) lo = alpha; else hi = alpha;
       double next = alpha - d1 / d2;
       if (!(next > lo && next < hi)) next = isinf(hi) ? 2 * alpha + 1 : 0.5 * (lo + hi);

@@ -58,9 +58,9 @@ def test_teacher_forced_env_step(capi):
     worst = 0.0
     for t in range(T):
         st = pool.state_arrays(pool.state_export())
-        rs = st["rstate"].reshape(-1)[: n * 32].reshape(n, 32)
+        rs = st["rstate"]                       # SoA [32, n]: qpos 0-8, qvel 9-17, warm 18-26
         for e in range(n):
-            orc.mjc_set(e, rs[e, :27], int(st["flags"][e] & 1), int(st["flags"][e] >> 1))
+            orc.mjc_set(e, rs[:27, e], int(st["flags"][e] & 1), int(st["flags"][e] >> 1))
         a = rng.uniform(-1, 1, size=(n, 6))
         g, w = pool.step(a), orc.step(a)
         for k in KEYS_EXACT:

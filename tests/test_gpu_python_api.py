@@ -126,11 +126,44 @@ def test_step_device_zero_copy(ep):
         np.testing.assert_array_equal(out["done"].cpu().numpy(), term | trunc)
 
 
+def test_async_mode_send_recv(ep):
+    """batch_size < num_envs (async_envpool.h:93-97): the loop of benchmark/test_envpool.py
+    (async_reset; recv -> send(action, env_id)).  Every recv returns exactly batch_size
+    rows; each row is checked, by env id, against what the oracle says that env's next
+    output must be."""
+    from oracle.oracle_lib import OraclePool
+
+    N, B = 24, 8
+    env = ep.make_gym("CartPole-v1", num_envs=N, batch_size=B, seed=4)
+    assert env.is_async
+    orc = OraclePool("CartPole", N, seed=4, max_episode_steps=500)
+    w = orc.reset()
+    exp_obs, exp_step = w["obs"].copy(), w["elapsed_step"].copy()
+    env.async_reset()
+    rng = np.random.default_rng(6)
+    for it in range(80):
+        obs, rew, term, trunc, info = env.recv()
+        ids = info["env_id"]
+        assert obs.shape == (B, 4) and len(set(ids.tolist())) == B
+        np.testing.assert_allclose(obs, exp_obs[ids], rtol=0, atol=1e-6)
+        np.testing.assert_array_equal(info["elapsed_step"], exp_step[ids])
+        if it % 7 == 3:
+            # two sends of B/2 rows: the next recv of these envs straddles two submissions
+            for part in (ids[: B // 2], ids[B // 2:]):
+                a = rng.integers(0, 2, size=len(part)).astype(np.int32)
+                w = orc.step(a, part)
+                exp_obs[part], exp_step[part] = w["obs"], w["elapsed_step"]
+                env.send(a, part)
+        else:
+            a = rng.integers(0, 2, size=B).astype(np.int32)
+            w = orc.step(a, ids)
+            exp_obs[ids], exp_step[ids] = w["obs"], w["elapsed_step"]
+            env.send(a, ids)
+
+
 def test_errors_and_engine_kwargs(ep):
     with pytest.raises(ValueError):
         ep.make_gym("CartPole-v1", num_envs=4, batch_size=2, gym_reset_return_info=False)
-    with pytest.raises(RuntimeError):
-        ep.make_gym("CartPole-v1", num_envs=4, batch_size=2)   # async mode: unsupported
     with pytest.raises(AssertionError):
         ep.make_gym("NoSuchEnv-v0", num_envs=1)
     env = ep.make_gym("CartPole-v1", num_envs=8, seed=1, precision="f32", env_id_offset=100)
