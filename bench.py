@@ -431,7 +431,9 @@ def run_reference(args):
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     K, W = args.steps, args.warmup
-    # bound the run to a few minutes: one reference step of 65536 envs is tens of ms
+    # same workload as our arm at this --gpus: num_envs per GPU x world envs in one pool
+    # (the reference has no multi-device mode; one process, every host core)
+    args.num_envs = args.num_envs * world
     cb = cpu_baseline(args, steps=K, warmup=W)
     n = args.num_envs
     out = {

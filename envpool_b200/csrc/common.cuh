@@ -117,6 +117,16 @@ struct Mt {
     own[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
     own[1] = make_uint4(cw[4], cw[5], cw[6], cw[7]);
     have = true;
+    // The NEXT regeneration (chunk c+1) will read sectors c+1 and c+50 -- both touched just
+    // now, so they sit in L2 -- and c+2, c+51, which are not.  Ask L2 for those two now
+    // (fire-and-forget): draws are rare events per env (a reset every ~20 steps, a slip
+    // refill every 8), so by the time they are needed they are an L2 hit instead of a DRAM
+    // round trip on the critical path of that step's kernel.
+    int c2 = c + 2, c51 = c + 51;
+    c2 = c2 >= 78 ? c2 - 78 : c2;
+    c51 = c51 >= 78 ? c51 - 78 : c51;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(sector(c2)));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(sector(c51)));
   }
   __device__ __forceinline__ uint32_t next() {
     const int k = idx & 7;

@@ -286,7 +286,7 @@ __device__ __forceinline__ void warp_chol_solve(const double* L, double* x, int 
   }
 }
 
-__device__ __forceinline__ void impedance(const double* solref, const double* solimp,
+__device__ __noinline__ void impedance(const double* solref, const double* solimp,
                                           double pos, double& imp, double& K, double& B) {
   double dmin = fmin(MAXIMP, fmax(MINIMP, solimp[0]));
   double dmax = fmin(MAXIMP, fmax(MINIMP, solimp[1]));
