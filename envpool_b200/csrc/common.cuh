@@ -65,22 +65,27 @@ struct OutView {
 // + 1 sector write per 8 draws, all loads in flight together.  The sequence is identical to
 // std::mt19937's.
 struct Mt {
-  uint32_t* tab;   // sv.mt
-  int64_t n;       // N
-  int eid;
-  int idx;         // next word to hand out, 0..623
-  uint32_t cw[8];  // register copy of the chunk idx lies in (raw words)
+  uint32_t* base;   // &mt[eid*8]: word 0 of chunk 0 of this env
+  int64_t cstride;  // words between consecutive chunks of one env (= 8*N)
+  int idx;          // next word to hand out, 0..623
+  uint32_t cw[8];   // register copy of the chunk idx lies in (raw words)
   bool have;
-  __device__ __forceinline__ Mt(const StateView& sv, int eid_)
-      : tab(sv.mt), n(sv.n_envs), eid(eid_), idx(sv.mt_idx[eid_]), have(false) {}
+  // split-phase first access (begin / next): loads issued early, consumed by the first draw
+  uint4 p_o0, p_o1, p_m0, p_m1;
+  uint32_t p_nx, p_m2;
+  int pending;  // 0 = nothing in flight, 1 = regeneration inputs, 2 = the current chunk
+  __device__ __forceinline__ Mt(const StateView& sv, int eid)
+      : base(sv.mt + (int64_t)eid * 8), cstride((int64_t)sv.n_envs * 8), idx(sv.mt_idx[eid]),
+        have(false), pending(0) {}
   // idx already loaded by the caller (issued together with the env-state loads so the
   // draw does not pay a second dependent round trip)
-  __device__ __forceinline__ Mt(const StateView& sv, int eid_, int idx_)
-      : tab(sv.mt), n(sv.n_envs), eid(eid_), idx(idx_), have(false) {}
+  __device__ __forceinline__ Mt(const StateView& sv, int eid, int idx_)
+      : base(sv.mt + (int64_t)eid * 8), cstride((int64_t)sv.n_envs * 8), idx(idx_),
+        have(false), pending(0) {}
   __device__ __forceinline__ void save(const StateView& sv, int e) { sv.mt_idx[e] = idx; }
 
   __device__ __forceinline__ uint4* sector(int chunk) const {
-    return reinterpret_cast<uint4*>(tab + ((int64_t)chunk * n + eid) * 8);
+    return reinterpret_cast<uint4*>(base + chunk * cstride);
   }
   static __device__ __forceinline__ uint32_t twist(uint32_t a, uint32_t b, uint32_t m) {
     uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
@@ -93,63 +98,113 @@ struct Mt {
     v ^= (v >> 18);
     return v;
   }
-  // regenerate chunk c in place; cw <- its new raw words
-  __device__ __forceinline__ void regen(int c) {
+  // Issue the loads the next draw will need and return without waiting for them: the
+  // caller runs unrelated work (the step arithmetic of the warp's non-resetting lanes)
+  // before the first draw, which then finds its operands already in registers.
+  __device__ __forceinline__ void begin() {
+    const int c = idx >> 3;
+    if ((idx & 7) == 0) {
+      load_regen_inputs(c);
+      pending = 1;
+    } else {
+      const uint4* own = sector(c);
+      p_o0 = own[0];
+      p_o1 = own[1];
+      pending = 2;
+    }
+  }
+  __device__ __forceinline__ void load_regen_inputs(int c) {
     int c1 = c + 1, c49 = c + 49, c50 = c + 50;
     c1 = c1 >= 78 ? c1 - 78 : c1;
     c49 = c49 >= 78 ? c49 - 78 : c49;
     c50 = c50 >= 78 ? c50 - 78 : c50;
-    uint4* own = sector(c);
-    const uint4 o0 = own[0], o1 = own[1];
-    const uint32_t nx = reinterpret_cast<const uint32_t*>(sector(c1))[0];
-    const uint4 m0 = sector(c49)[1];                       // words 4..7 of chunk c+49
-    const uint4 m1 = sector(c50)[0];                       // words 0..3 of chunk c+50
-    const uint32_t m2 = reinterpret_cast<const uint32_t*>(sector(c50))[4];  // word 4
-    // word i+397 for i = 8c+k, k = 0..7: chunk c+49 words 5,6,7 then chunk c+50 words 0..4
-    cw[0] = twist(o0.x, o0.y, m0.y);
-    cw[1] = twist(o0.y, o0.z, m0.z);
-    cw[2] = twist(o0.z, o0.w, m0.w);
-    cw[3] = twist(o0.w, o1.x, m1.x);
-    cw[4] = twist(o1.x, o1.y, m1.y);
-    cw[5] = twist(o1.y, o1.z, m1.z);
-    cw[6] = twist(o1.z, o1.w, m1.w);
-    cw[7] = twist(o1.w, nx, m2);
-    own[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
-    own[1] = make_uint4(cw[4], cw[5], cw[6], cw[7]);
-    have = true;
-    // The NEXT regeneration (chunk c+1) will read sectors c+1 and c+50 -- both touched just
-    // now, so they sit in L2 -- and c+2, c+51, which are not.  Ask L2 for those two now
-    // (fire-and-forget): draws are rare events per env (a reset every ~20 steps, a slip
-    // refill every 8), so by the time they are needed they are an L2 hit instead of a DRAM
-    // round trip on the critical path of that step's kernel.
-    int c2 = c + 2, c51 = c + 51;
-    c2 = c2 >= 78 ? c2 - 78 : c2;
-    c51 = c51 >= 78 ? c51 - 78 : c51;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(sector(c2)));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(sector(c51)));
+    const uint4* own = sector(c);
+    const uint4* s50 = sector(c50);
+    p_o0 = own[0];
+    p_o1 = own[1];
+    p_nx = reinterpret_cast<const uint32_t*>(sector(c1))[0];
+    p_m0 = sector(c49)[1];                              // words 4..7 of chunk c+49
+    p_m1 = s50[0];                                      // words 0..3 of chunk c+50
+    p_m2 = reinterpret_cast<const uint32_t*>(s50)[4];   // word 4
   }
-  __device__ __forceinline__ uint32_t next() {
-    const int k = idx & 7;
-    if (k == 0) {
-      regen(idx >> 3);
+  // Make cw the raw words of the chunk idx lies in: regenerate it if idx enters it now,
+  // else (first access of this kernel) read it back.  The ONE place the table is touched.
+  __device__ __forceinline__ void enter_chunk() {
+    const int c = idx >> 3;
+    if ((idx & 7) == 0) {
+      if (pending != 1) load_regen_inputs(c);
+      pending = 0;
+      const uint4 o0 = p_o0, o1 = p_o1, m0 = p_m0, m1 = p_m1;
+      // word i+397 for i = 8c+k, k = 0..7: chunk c+49 words 5,6,7 then chunk c+50 words 0..4
+      cw[0] = twist(o0.x, o0.y, m0.y);
+      cw[1] = twist(o0.y, o0.z, m0.z);
+      cw[2] = twist(o0.z, o0.w, m0.w);
+      cw[3] = twist(o0.w, o1.x, m1.x);
+      cw[4] = twist(o1.x, o1.y, m1.y);
+      cw[5] = twist(o1.y, o1.z, m1.z);
+      cw[6] = twist(o1.z, o1.w, m1.w);
+      cw[7] = twist(o1.w, p_nx, p_m2);
+      uint4* own = sector(c);
+      own[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+      own[1] = make_uint4(cw[4], cw[5], cw[6], cw[7]);
+      have = true;
+      // The NEXT regeneration (chunk c+1) will read sectors c+1 and c+50 -- both touched
+      // just now, so they sit in L2 -- and c+2, c+51, which are not.  Ask L2 for those two
+      // now (fire-and-forget): draws are rare events per env (a reset every ~20 steps, a slip
+      // refill every 8), so by the time they are needed they are an L2 hit, not a DRAM
+      // round trip on the critical path of that step's kernel.
+      int c2 = c + 2, c51 = c + 51;
+      c2 = c2 >= 78 ? c2 - 78 : c2;
+      c51 = c51 >= 78 ? c51 - 78 : c51;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(sector(c2)));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(sector(c51)));
     } else if (!have) {
-      const uint4* own = sector(idx >> 3);
-      const uint4 o0 = own[0], o1 = own[1];
-      cw[0] = o0.x; cw[1] = o0.y; cw[2] = o0.z; cw[3] = o0.w;
-      cw[4] = o1.x; cw[5] = o1.y; cw[6] = o1.z; cw[7] = o1.w;
+      if (pending != 2) {
+        const uint4* own = sector(c);
+        p_o0 = own[0];
+        p_o1 = own[1];
+      }
+      pending = 0;
+      cw[0] = p_o0.x; cw[1] = p_o0.y; cw[2] = p_o0.z; cw[3] = p_o0.w;
+      cw[4] = p_o1.x; cw[5] = p_o1.y; cw[6] = p_o1.z; cw[7] = p_o1.w;
       have = true;
     }
-    uint32_t v = cw[0];
-#pragma unroll
-    for (int j = 1; j < 8; ++j) v = (k == j) ? cw[j] : v;
-    idx = (idx + 1 == kMtN) ? 0 : idx + 1;
-    return temper(v);
   }
-  // K consecutive draws (same sequence as K next() calls)
+  __device__ __forceinline__ void advance(int k) {
+    idx += k;
+    idx = idx >= kMtN ? idx - kMtN : idx;
+  }
+  // K consecutive draws (the sequence K calls of std::mt19937::operator() would give).
+  // Fast path: K is a power of two <= 8 and the read position is K-aligned -- true for every
+  // env that always draws in groups of K (CartPole/Acrobot 8, Pendulum 4, MountainCar 2,
+  // per-step single draws) -- so the K words sit in one chunk at cw[k..k+K).  Otherwise
+  // word by word, in a rolled loop (rare: Blackjack's dealer, HalfCheetah's 18+ draws).
   template <int K>
   __device__ __forceinline__ void next_batch(uint32_t (&out)[K]) {
+    const int k = idx & 7;
+    if ((K == 1 || K == 2 || K == 4 || K == 8) && (k & (K - 1)) == 0) {
+      enter_chunk();
 #pragma unroll
-    for (int k = 0; k < K; ++k) out[k] = next();
+      for (int j = 0; j < K; ++j) {
+        uint32_t v = cw[j];
+#pragma unroll
+        for (int b = K; b < 8; b += K) v = (k == b) ? cw[b + j] : v;
+        out[j] = temper(v);
+      }
+      advance(K);
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < K; ++j) {
+        uint32_t w[1];
+        next_batch<1>(w);
+        out[j] = w[0];
+      }
+    }
+  }
+  __device__ __forceinline__ uint32_t next() {
+    uint32_t w[1];
+    next_batch<1>(w);
+    return w[0];
   }
 
   // std::generate_canonical<double,53> (libstdc++ 13 bits/random.tcc:3349-3381) from two
@@ -277,36 +332,31 @@ __device__ __forceinline__ void env_step(const StateView& sv, int eid, int& flag
                                          bool force_reset, StepOut& so, int& mt_idx) {
   int done = flags & 1;
   int cur = flags >> 1;
-  bool reset = force_reset || done;
-  if (reset) {
+  const bool reset = force_reset || done;
+  // A warp usually holds both resetting and stepping lanes (CartPole: ~5 % of envs reset per
+  // step, so 80 % of warps do).  Order of work: resetting lanes ISSUE their mt19937 loads,
+  // then the stepping lanes run their arithmetic, then the resetting lanes consume the loads
+  // -- the memory latency of a reset hides behind the step math instead of adding to it.
+  Mt rng(sv, eid, mt_idx);
+  if (Env::kRngInReset && reset) rng.begin();
+  if (!reset) {
+    ++cur;
+    Env::step(sv, s, a, cur, done, Env::kRngInStep ? &rng : nullptr, so);
+  } else {
     cur = 0;
     done = 0;
-    if (Env::kRngInReset) {
-      Mt rng(sv, eid, mt_idx);
-      Env::reset(sv, s, &rng, so);
-      mt_idx = rng.idx;
-    } else {
-      Env::reset(sv, s, nullptr, so);
-    }
-  } else {
-    ++cur;
-    if (Env::kRngInStep) {
-      Mt rng(sv, eid, mt_idx);
-      Env::step(sv, s, a, cur, done, &rng, so);
-      mt_idx = rng.idx;
-    } else {
-      Env::step(sv, s, a, cur, done, nullptr, so);
-    }
+    Env::reset(sv, s, Env::kRngInReset ? &rng : nullptr, so);
   }
+  if (Env::kRngInReset || Env::kRngInStep) mt_idx = rng.idx;
   flags = (cur << 1) | done;
 }
 
 // Single sync step of a batch: thread `row` handles env env_ids[row] (identity if NULL).
-template <class Env>
-__global__ void __launch_bounds__(kBlock)
+template <class Env, int kB = kBlock>
+__global__ void __launch_bounds__(kB)
 step_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ action,
             const int32_t* __restrict__ env_ids, int n, int force_reset) {
-  int row = blockIdx.x * kBlock + threadIdx.x;
+  int row = blockIdx.x * kB + threadIdx.x;
   bool active = row < n;
   typename Env::State s;
   StepOut so;
@@ -338,7 +388,7 @@ step_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ acti
                  sv.max_steps);
   }
   if constexpr (Env::kBlockObs) {
-    Env::block_write_obs(ov, (int64_t)blockIdx.x * kBlock, n, active, s, so);
+    Env::template block_write_obs<kB>(ov, (int64_t)blockIdx.x * kB, n, active, s, so);
   } else if (active) {
     Env::write_obs(sv, ov, row, s, so);
   }
@@ -376,8 +426,9 @@ rollout_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ a
                    sv.max_steps);
     }
     if constexpr (Env::kBlockObs) {
-      Env::block_write_obs(ov, (int64_t)t * ov.t_stride_rows + (int64_t)blockIdx.x * kBlock,
-                           (int64_t)t * ov.t_stride_rows + n, active, s, so);
+      Env::template block_write_obs<kBlock>(
+          ov, (int64_t)t * ov.t_stride_rows + (int64_t)blockIdx.x * kBlock,
+          (int64_t)t * ov.t_stride_rows + n, active, s, so);
     } else if (active) {
       Env::write_obs(sv, ov, row, s, so);
     }
@@ -411,11 +462,23 @@ inline bool pdl_enabled() {
   return on;
 }
 
-template <class Env>
-cudaError_t launch_step(const LaunchArgs& a) {
+// CTA size of the single-step kernel: small batches are latency-bound and want many small
+// CTAs spread evenly over the 148 SMs, large batches want fewer, fatter CTAs.
+// ENVPOOL_B200_STEP_BLOCK overrides (64 | 128 | 256).
+inline int step_block_for(int n) {
+  static const int forced = [] {
+    const char* e = getenv("ENVPOOL_B200_STEP_BLOCK");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced == 64 || forced == 128 || forced == 256) return forced;
+  return n <= 148 * 8 * 128 ? 64 : 128;
+}
+
+template <class Env, int kB>
+cudaError_t launch_step_b(const LaunchArgs& a) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((a.n + kBlock - 1) / kBlock);
-  cfg.blockDim = dim3(kBlock);
+  cfg.gridDim = dim3((a.n + kB - 1) / kB);
+  cfg.blockDim = dim3(kB);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = a.stream;
   cudaLaunchAttribute attr[1];
@@ -428,9 +491,18 @@ cudaError_t launch_step(const LaunchArgs& a) {
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(a.stream, &cap);
   cfg.numAttrs = (pdl_enabled() && cap == cudaStreamCaptureStatusNone) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, step_kernel<Env>, a.sv, a.ov,
+  return cudaLaunchKernelEx(&cfg, step_kernel<Env, kB>, a.sv, a.ov,
                             static_cast<const typename Env::Act*>(a.action), a.env_ids, a.n,
                             a.force_reset);
+}
+
+template <class Env>
+cudaError_t launch_step(const LaunchArgs& a) {
+  switch (step_block_for(a.n)) {
+    case 64: return launch_step_b<Env, 64>(a);
+    case 256: return launch_step_b<Env, 256>(a);
+    default: return launch_step_b<Env, 128>(a);
+  }
 }
 template <class Env>
 cudaError_t launch_rollout(const LaunchArgs& a) {

@@ -141,20 +141,21 @@ struct Catch {
                                                    const State&,
                                                    const StepOut&) {}
   // rows [row0, row0+kBlock) ∩ [.., row_end) of the obs column are written by the CTA.
+  template <int kB>
   static __device__ __forceinline__ void block_write_obs(const OutView& ov, int64_t row0,
                                                          int64_t row_end, bool active,
                                                          const State& s, const StepOut&) {
-    __shared__ int16_t cells[kBlock][2];
+    __shared__ int16_t cells[kB][2];
     int x = s.w & 0xff, y = (s.w >> 8) & 0xff, paddle = (s.w >> 16) & 0xff;
     cells[threadIdx.x][0] = active ? (int16_t)(x * kW + y) : (int16_t)-1;
     cells[threadIdx.x][1] = active ? (int16_t)((kH - 1) * kW + paddle) : (int16_t)-1;
     __syncthreads();
     if (ov.env[0]) {
       int64_t rows = row_end - row0;
-      if (rows > kBlock) rows = kBlock;
+      if (rows > kB) rows = kB;
       int nvec = (int)(rows * kCells / 2);  // float2 chunks (kCells is even)
       float2* out = reinterpret_cast<float2*>(static_cast<float*>(ov.env[0]) + row0 * kCells);
-      for (int v = threadIdx.x; v < nvec; v += kBlock) {
+      for (int v = threadIdx.x; v < nvec; v += kB) {
         int e = (2 * v) / kCells;
         int c = (2 * v) - e * kCells;
         int b = cells[e][0], p = cells[e][1];
