@@ -56,6 +56,21 @@ static int fail(int code, const std::string& msg) {
       return fail(EPB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+// Every entry point runs on the pool's device but leaves the caller's current device as it
+// found it (a host process may drive several pools / use torch on another GPU).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t status;
+  explicit DeviceGuard(int dev) {
+    status = cudaGetDevice(&prev);
+    if (status == cudaSuccess && prev != dev) status = cudaSetDevice(dev);
+    else if (status == cudaSuccess) prev = -1;  // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 struct Key {
   const char* name;
   int dtype, ndim, shape[3], row_bytes;
@@ -266,7 +281,8 @@ int launch_batch(epb_pool* p, const void* d_action, const int32_t* d_ids, int n,
 int host_submit(epb_pool* p, const void* action, const int32_t* env_ids, int n,
                 int force_reset) {
   if (n <= 0 || n > p->N) return fail(EPB_ERR_INVALID, "batch rows must be in [1, num_envs]");
-  EPB_CUDA(cudaSetDevice(p->cfg.device));
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
   const int f = p->stage_flip;
   p->stage_flip ^= 1;
   // the staging pair alternates; wait until the copy that last used this half is done
@@ -353,7 +369,8 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
   int ndev = 0;
   EPB_CUDA(cudaGetDeviceCount(&ndev));
   if (cfg->device < 0 || cfg->device >= ndev) return fail(EPB_ERR_INVALID, "bad device ordinal");
-  EPB_CUDA(cudaSetDevice(cfg->device));
+  DeviceGuard guard(cfg->device);
+  EPB_CUDA(guard.status);
 
   epb_pool* p = new epb_pool();
   p->kind = kind;
@@ -468,7 +485,7 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
 
 int epb_destroy(epb_pool* p) {
   if (!p) return EPB_OK;
-  cudaSetDevice(p->cfg.device);
+  DeviceGuard guard(p->cfg.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   for (Pending& pd : p->pending)
     if (!pd.ready) cudaEventDestroy(pd.ev);
@@ -645,14 +662,16 @@ int epb_step_device(epb_pool* p, const void* d_action, const int32_t* d_env_ids,
   if (!p) return fail(EPB_ERR_INVALID, "null pool");
   if (n <= 0 || n > p->N) return fail(EPB_ERR_INVALID, "batch rows must be in [1, num_envs]");
   if (!d_action) return fail(EPB_ERR_INVALID, "action is NULL");
-  EPB_CUDA(cudaSetDevice(p->cfg.device));
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
   return launch_batch(p, d_action, d_env_ids, n, 0, p->d_slab, s);
 }
 int epb_reset_device(epb_pool* p, const int32_t* d_env_ids, int n, void* stream) {
   if (!p) return fail(EPB_ERR_INVALID, "null pool");
   if (n <= 0 || n > p->N) return fail(EPB_ERR_INVALID, "batch rows must be in [1, num_envs]");
-  EPB_CUDA(cudaSetDevice(p->cfg.device));
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
   return launch_batch(p, nullptr, d_env_ids, n, 1, p->d_slab, s);
 }
@@ -666,7 +685,8 @@ int epb_rollout_device(epb_pool* p, const void* d_actions, int T, void* const* d
                        void* stream) {
   if (!p || !d_actions || !d_cols) return fail(EPB_ERR_INVALID, "null argument");
   if (T <= 0) return fail(EPB_ERR_INVALID, "T must be positive");
-  EPB_CUDA(cudaSetDevice(p->cfg.device));
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
   OutView ov{};
   ov.env_id = static_cast<int32_t*>(d_cols[0]);
@@ -700,7 +720,8 @@ int epb_step_many_device(epb_pool* p, const void* d_actions, int T_stream, int t
                          int use_graph, void* stream) {
   if (!p || !d_actions) return fail(EPB_ERR_INVALID, "null argument");
   if (T_stream <= 0 || K <= 0 || t0 < 0) return fail(EPB_ERR_INVALID, "bad step-chain shape");
-  EPB_CUDA(cudaSetDevice(p->cfg.device));
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
   const size_t row = (size_t)p->act.row_bytes * p->N;
   auto chain = [&](cudaStream_t st) -> int {
@@ -744,7 +765,8 @@ int epb_step_many_device(epb_pool* p, const void* d_actions, int T_stream, int t
 
 int epb_sync(epb_pool* p) {
   if (!p) return fail(EPB_ERR_INVALID, "null pool");
-  EPB_CUDA(cudaSetDevice(p->cfg.device));
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
   EPB_CUDA(cudaStreamSynchronize(p->stream));
   return EPB_OK;
 }
@@ -766,14 +788,16 @@ int epb_state_layout(const epb_pool* p, int64_t* out) {
 }
 int epb_state_export(epb_pool* p, void* host_dst) {
   if (!p || !host_dst) return fail(EPB_ERR_INVALID, "null argument");
-  EPB_CUDA(cudaSetDevice(p->cfg.device));
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
   EPB_CUDA(cudaStreamSynchronize(p->stream));
   EPB_CUDA(cudaMemcpy(host_dst, p->d_state_blob, (size_t)p->state_bytes, cudaMemcpyDeviceToHost));
   return EPB_OK;
 }
 int epb_state_import(epb_pool* p, const void* host_src) {
   if (!p || !host_src) return fail(EPB_ERR_INVALID, "null argument");
-  EPB_CUDA(cudaSetDevice(p->cfg.device));
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
   EPB_CUDA(cudaStreamSynchronize(p->stream));
   EPB_CUDA(cudaMemcpy(p->d_state_blob, host_src, (size_t)p->state_bytes, cudaMemcpyHostToDevice));
   return EPB_OK;
