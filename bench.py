@@ -268,20 +268,43 @@ def run_allgather(args, torch, dist, pool, actions, dev, stream, world):
 
     n, T = pool.n, actions.shape[0]
     slab = _torch_view(pool.outputs_device_ptr(), (pool.slab_bytes,), torch.uint8, dev.index)
-    full = None
-    steps = int(min(max(args.steps, 50), 2000))
-    with torch.cuda.stream(stream):
-        for k in range(20):
-            pool.step_device(actions[k % T])
-            full = all_gather_packed(slab, full)
+    full = torch.empty((world, pool.slab_bytes), dtype=torch.uint8, device=dev)
+    steps = int(min(max(args.steps, 64), 2048)) // 64 * 64
+    chunk = 64
+    side = torch.cuda.Stream(device=dev)
+
+    def body(k0):
+        for k in range(chunk):
+            pool.step_device(actions[(k0 + k) % T],
+                             stream=torch.cuda.current_stream(dev).cuda_stream)
+            all_gather_packed(slab, full)
+
+    # warm-up (also initialises NCCL's channels for this size), then capture `chunk` steps
+    # -- step kernel + all-gather each -- into one CUDA graph so that the loop is not bound by
+    # the host's launch rate
+    mode = "cuda-graph replay of 64-step chunks"
+    with torch.cuda.stream(side):
+        body(0)
+        torch.cuda.synchronize()
+        graph = None
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                body(0)
+            graph = g
+        except Exception as exc:  # capture unsupported: fall back to eager launches
+            mode = f"eager launches (graph capture failed: {type(exc).__name__})"
+            torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for k in range(steps):
-            pool.step_device(actions[k % T])
-            full = all_gather_packed(slab, full)
-        ev1.record(stream)
+        ev0.record(side)
+        for c in range(steps // chunk):
+            if graph is not None:
+                graph.replay()
+            else:
+                body(c * chunk)
+        ev1.record(side)
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     tt = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -291,7 +314,7 @@ def run_allgather(args, torch, dist, pool, actions, dev, stream, world):
     return {"value": n * world * steps / (ms * 1e-3), "unit": "env-steps/s", "steps": steps,
             "ms_per_step": ms / steps, "allgather_bytes_in_per_gpu_per_step": gathered,
             "nvlink_gbs_in_per_gpu": gathered * steps / (ms * 1e-3) / 1e9,
-            "api": "step_device + one ncclAllGather of the packed output slab per step"}
+            "api": "step_device + one ncclAllGather of the packed output slab per step; " + mode}
 
 
 def run_rollout(args, torch, pool, actions, dev):

@@ -26,8 +26,6 @@ struct Arrow {
   double Cb[3][3], Cf[3][3];  // [leg dof][root dof]
 };
 
-__device__ __forceinline__ int sidx(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
-
 // y = A x for packed symmetric 3x3
 __device__ __forceinline__ void symv3(const double* A, const double* x, double* y) {
   y[0] = A[0] * x[0] + A[1] * x[1] + A[3] * x[2];
@@ -37,7 +35,6 @@ __device__ __forceinline__ void symv3(const double* A, const double* x, double* 
 
 // y = H x for the block-arrow matrix; x, y are [root(3) | back(3) | front(3)]
 __device__ __forceinline__ void arrow_mv(const Arrow& H, const double* x, double* y) {
-  double t[3];
   symv3(H.R, x, y);
   symv3(H.Ab, x + 3, y + 3);
   symv3(H.Af, x + 6, y + 6);
@@ -51,7 +48,6 @@ __device__ __forceinline__ void arrow_mv(const Arrow& H, const double* x, double
     y[3 + l] += H.Cb[l][0] * x[0] + H.Cb[l][1] * x[1] + H.Cb[l][2] * x[2];
     y[6 + l] += H.Cf[l][0] * x[0] + H.Cf[l][1] * x[1] + H.Cf[l][2] * x[2];
   }
-  (void)t;
 }
 
 // in-place Cholesky of a packed symmetric 3x3: A = L L^T; the diagonal of L is stored

@@ -458,6 +458,8 @@ static void make_constraints(const mjc_model* m, const double* q, const double* 
 }
 
 /* ------------------------------------------------------------------------- solver --- */
+static long g_ls_hist[64]; /* diagnostics: histogram of line-search evaluations per Newton step */
+void mjc_debug_ls_hist(long* out) { for (int i = 0; i < 64; ++i) { out[i] = g_ls_hist[i]; g_ls_hist[i] = 0; } }
 /* cost(a) = 1/2 (a - a_s)^T M (a - a_s) + sum_i 1/2 D_i min(0, J_i a - aref_i)^2 */
 static double constraint_cost(const efc_t* e, const double* jar) {
   double c = 0;
@@ -563,7 +565,9 @@ static void solve_newton(const mjc_model* m, const efc_t* e, const double* M,
     for (int i = 0; i < NV; ++i) snorm += search[i] * search[i];
     const double gtol = m->tolerance * 0.01 * sqrt(snorm) / scale;
     double lo = 0, hi = INFINITY, alpha = 0;
+    int ls_evals = 0;
     for (int k = 0; k < m->ls_iter; ++k) {
+      ++ls_evals;
       double d1 = q1 + alpha * q2, d2 = q2;
       for (int r = 0; r < n; ++r) {
         double x = jar[r] + alpha * Jv[r];
@@ -579,6 +583,7 @@ static void solve_newton(const mjc_model* m, const efc_t* e, const double* M,
       if (next == alpha) break;
       alpha = next;
     }
+    g_ls_hist[ls_evals < 63 ? ls_evals : 63]++;
     if (alpha == 0) break;
     for (int i = 0; i < NV; ++i) qacc[i] += alpha * search[i];
   }

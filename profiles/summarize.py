@@ -95,6 +95,35 @@ def main():
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             lines.append(f"| `{k[:70]}` | {len(v)} | {fmt(sum(v) / len(v), 0)} | "
                          f"{fmt(100 * sum(v) / tot, 1)} % |")
+    for g in (2, 4, 8):
+        mg = os.path.join(ROOT, "gpurun_out", f"r1_mg{g}")
+        files = sorted(glob.glob(os.path.join(mg, "bench_*.json")))
+        if not files:
+            continue
+        lines.append(f"\n## {g} x B200, one rank per GPU (`profiles/run_multigpu.sh {g}`): env-id "
+                     "sharding; `value` has no data-path collective, `with_allgather` adds one "
+                     "NCCL all-gather of the packed outputs per step\n")
+        lines.append("| workload | G env-steps/s (box) | us/step | + all-gather: G/s | us/step | "
+                     "NVLink GB/s in per GPU | e2e M/s (box) |")
+        lines.append("|---|---|---|---|---|---|---|")
+        with open(os.path.join(DST, f"r1_bench_lines_{g}gpu.jsonl"), "w") as f:
+            for pth in files:
+                d = load(pth)
+                if not d:
+                    continue
+                f.write(json.dumps({"file": os.path.basename(pth), **d}) + "\n")
+                ag = d.get("with_allgather") or {}
+                lines.append("| {} | {} | {} | {} | {} | {} | {} |".format(
+                    d["config"]["workload"], fmt(d["value"] / 1e9, 3),
+                    fmt(d["ms_per_step"] * 1e3),
+                    fmt(ag["value"] / 1e9, 3) if ag else "-",
+                    fmt(ag["ms_per_step"] * 1e3) if ag else "-",
+                    fmt(ag.get("nvlink_gbs_in_per_gpu"), 0) if ag else "-",
+                    fmt(d["e2e"]["value"] / 1e6, 1) if d.get("e2e") else "-"))
+        st = os.path.join(mg, "pytest_sharded.txt")
+        if os.path.exists(st):
+            lines.append(f"\n`pytest tests/test_gpu_sharded.py` on this box: "
+                         f"`{open(st).read().strip().splitlines()[-1]}`")
     traffic = {}
     for rep, label, key in (("prof_step_cartpole65536", "step_kernel<CartPole<double>>, N=65536",
                              "CartPole-v1:65536:f64"),
