@@ -34,8 +34,11 @@ ABI_SYMBOLS = [
     "epb_recv", "epb_step_device", "epb_reset_device", "epb_outputs_device",
     "epb_rollout_device", "epb_step_many_device", "epb_sync", "epb_stream", "epb_state_bytes",
     "epb_state_layout", "epb_state_export", "epb_state_import", "epb_launch_count",
-    "epb_bytes_per_env_step",
+    "epb_bytes_per_env_step", "epb_exchange_init", "epb_exchange_base", "epb_exchange_attach",
+    "epb_exchange_attach_ipc", "epb_step_exchange_device", "epb_exchange_wait",
+    "epb_exchange_status",
 ]
+IPC_HANDLE_BYTES = 64
 
 
 class EpbConfig(ctypes.Structure):
@@ -104,6 +107,13 @@ def load_library() -> ctypes.CDLL:
     L.epb_launch_count.restype = ctypes.c_int64
     L.epb_launch_count.argtypes = [vp]
     L.epb_bytes_per_env_step.argtypes = [vp]
+    L.epb_exchange_init.argtypes = [vp, ci, ci, vp]
+    L.epb_exchange_base.argtypes = [vp, pp, ctypes.POINTER(ctypes.c_int64)]
+    L.epb_exchange_attach.argtypes = [vp, pp]
+    L.epb_exchange_attach_ipc.argtypes = [vp, vp]
+    L.epb_step_exchange_device.argtypes = [vp, vp, vp]
+    L.epb_exchange_wait.argtypes = [vp, vp, pp]
+    L.epb_exchange_status.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ci)]
     _lib = L
     return L
 
@@ -304,6 +314,48 @@ class CPool:
         _check(self.lib.epb_step_many_device(self.h, d_actions.data_ptr(),
                                              d_actions.shape[0], t0, K,
                                              1 if use_graph else 0, stream))
+
+    # ------------------------------------------------------------- peer exchange
+    def exchange_init(self, world: int, rank: int) -> bytes:
+        """Allocate this rank's gather buffer; returns its 64-byte CUDA IPC handle."""
+        buf = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(self.lib.epb_exchange_init(self.h, world, rank, buf))
+        self.world, self.rank = world, rank
+        return bytes(buf.raw)
+
+    def exchange_base(self) -> int:
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        _check(self.lib.epb_exchange_base(self.h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value
+
+    def exchange_attach(self, peer_bases: List[int]):
+        """Same-process peers: raw base pointers of every rank's gather buffer."""
+        arr = (ctypes.c_void_p * len(peer_bases))(*peer_bases)
+        _check(self.lib.epb_exchange_attach(self.h, arr))
+
+    def exchange_attach_ipc(self, handles: List[bytes]):
+        """One process per GPU: the IPC handles of all ranks, rank order."""
+        blob = b"".join(handles)
+        if len(blob) != IPC_HANDLE_BYTES * len(handles):
+            raise ValueError("every IPC handle must be 64 bytes")
+        _check(self.lib.epb_exchange_attach_ipc(self.h, blob))
+
+    def step_exchange(self, d_action, stream=None):
+        """d_action None = forced reset of all envs."""
+        pa = None if d_action is None else (
+            d_action.data_ptr() if hasattr(d_action, "data_ptr") else int(d_action))
+        _check(self.lib.epb_step_exchange_device(self.h, pa, stream))
+
+    def exchange_wait(self, stream=None) -> int:
+        """Enqueue the wait for all peers; returns the device pointer of [world][slab]."""
+        p = ctypes.c_void_p()
+        _check(self.lib.epb_exchange_wait(self.h, stream, ctypes.byref(p)))
+        return p.value
+
+    def exchange_status(self):
+        steps, bad = ctypes.c_int64(), ctypes.c_int()
+        _check(self.lib.epb_exchange_status(self.h, ctypes.byref(steps), ctypes.byref(bad)))
+        return int(steps.value), bool(bad.value)
 
     def sync(self):
         _check(self.lib.epb_sync(self.h))

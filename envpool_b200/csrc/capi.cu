@@ -16,6 +16,7 @@
 
 #include "../../include/envpool_b200.h"
 #include "common.cuh"
+#include "exchange.cuh"
 #include "mujoco.cuh"
 
 namespace epb {
@@ -105,6 +106,7 @@ struct epb_pool {
   void* d_state_blob = nullptr;  // flags | mt_idx | istate | rstate | mt | (mujoco extras)
   int64_t state_bytes = 0;
   char* d_slab = nullptr;
+  char* d_last = nullptr;  // slab the most recent *_device launch wrote (d_slab or a gather slice)
   void* d_action = nullptr;
   int32_t* d_ids = nullptr;
   // pinned host staging
@@ -133,6 +135,14 @@ struct epb_pool {
   std::vector<GraphEntry> graphs;
   int64_t launches = 0;
   int bytes_per_step = 0;
+  // peer exchange (exchange.cuh): gather[2][world][slab] | flags[world] | ctl
+  char* x_base = nullptr;
+  int x_world = 0, x_rank = 0;
+  int64_t x_flags_off = 0, x_ctl_off = 0, x_bytes = 0;
+  char* x_peer[kMaxPeers] = {};
+  bool x_ipc[kMaxPeers] = {};
+  bool x_attached = false;
+  uint64_t x_steps = 0;  // host count of exchanged steps; parity picks the gather half
 
   OutView slab_view(char* base) const {
     OutView ov{};
@@ -257,6 +267,7 @@ int get_event(epb_pool* p, cudaEvent_t* ev) {
 // Launch one batch step on `stream`.  d_action/d_ids are device pointers.
 int launch_batch(epb_pool* p, const void* d_action, const int32_t* d_ids, int n,
                  int force_reset, char* d_slab, cudaStream_t stream) {
+  p->d_last = d_slab;
   if (p->kind == EPB_HALF_CHEETAH) {
     EPB_CUDA(mjc_launch_step(p->mjc, p->sv, p->slab_view(d_slab),
                              static_cast<const double*>(d_action), d_ids, n, force_reset,
@@ -498,6 +509,9 @@ int epb_destroy(epb_pool* p) {
   }
   for (auto& g : p->graphs) cudaGraphExecDestroy(g.exec);
   if (p->mjc) mjc_pool_destroy(p->mjc);
+  for (int g = 0; g < kMaxPeers; ++g)
+    if (p->x_ipc[g] && p->x_peer[g]) cudaIpcCloseMemHandle(p->x_peer[g]);
+  if (p->x_base) cudaFree(p->x_base);
   if (p->d_state_blob) cudaFree(p->d_state_blob);
   if (p->d_slab) cudaFree(p->d_slab);
   if (p->d_action) cudaFree(p->d_action);
@@ -677,7 +691,7 @@ int epb_reset_device(epb_pool* p, const int32_t* d_env_ids, int n, void* stream)
 }
 int epb_outputs_device(const epb_pool* p, void** d_slab) {
   if (!p || !d_slab) return fail(EPB_ERR_INVALID, "null argument");
-  *d_slab = p->d_slab;
+  *d_slab = p->d_last ? p->d_last : p->d_slab;
   return EPB_OK;
 }
 
@@ -760,6 +774,123 @@ int epb_step_many_device(epb_pool* p, const void* d_actions, int T_stream, int t
   }
   EPB_CUDA(cudaGraphLaunch(exec, s));
   p->launches += K;
+  return EPB_OK;
+}
+
+// ---- peer exchange ---------------------------------------------------------------------
+int epb_exchange_init(epb_pool* p, int world, int rank, void* ipc_handle_out) {
+  if (!p) return fail(EPB_ERR_INVALID, "null pool");
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(EPB_ERR_INVALID, "exchange: world must be in [1,16] and rank in [0,world)");
+  if (p->x_base) return fail(EPB_ERR_STATE, "exchange already initialised");
+  static_assert(sizeof(cudaIpcMemHandle_t) == EPB_IPC_HANDLE_BYTES, "IPC handle size");
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
+  p->x_flags_off = 2 * (int64_t)world * p->slab_bytes;
+  p->x_ctl_off = p->x_flags_off + 256;
+  p->x_bytes = p->x_ctl_off + 256;
+  EPB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->x_base), (size_t)p->x_bytes));
+  EPB_CUDA(cudaMemset(p->x_base, 0, (size_t)p->x_bytes));
+  EPB_CUDA(cudaDeviceSynchronize());
+  p->x_world = world;
+  p->x_rank = rank;
+  p->x_peer[rank] = p->x_base;
+  p->x_attached = (world == 1);
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t h;
+    EPB_CUDA(cudaIpcGetMemHandle(&h, p->x_base));
+    memcpy(ipc_handle_out, &h, sizeof(h));
+  }
+  return EPB_OK;
+}
+int epb_exchange_base(const epb_pool* p, void** base, int64_t* bytes) {
+  if (!p || !base) return fail(EPB_ERR_INVALID, "null argument");
+  if (!p->x_base) return fail(EPB_ERR_STATE, "exchange not initialised");
+  *base = p->x_base;
+  if (bytes) *bytes = p->x_bytes;
+  return EPB_OK;
+}
+int epb_exchange_attach(epb_pool* p, void* const* peer_bases) {
+  if (!p || !peer_bases) return fail(EPB_ERR_INVALID, "null argument");
+  if (!p->x_base) return fail(EPB_ERR_STATE, "exchange not initialised");
+  for (int g = 0; g < p->x_world; ++g) {
+    if (g == p->x_rank) continue;
+    if (!peer_bases[g]) return fail(EPB_ERR_INVALID, "exchange: null peer base");
+    p->x_peer[g] = static_cast<char*>(peer_bases[g]);
+  }
+  p->x_attached = true;
+  return EPB_OK;
+}
+int epb_exchange_attach_ipc(epb_pool* p, const void* ipc_handles) {
+  if (!p || !ipc_handles) return fail(EPB_ERR_INVALID, "null argument");
+  if (!p->x_base) return fail(EPB_ERR_STATE, "exchange not initialised");
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
+  for (int g = 0; g < p->x_world; ++g) {
+    if (g == p->x_rank || p->x_ipc[g]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(ipc_handles) + (size_t)g * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    EPB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->x_peer[g] = static_cast<char*>(ptr);
+    p->x_ipc[g] = true;
+  }
+  p->x_attached = true;
+  return EPB_OK;
+}
+int epb_step_exchange_device(epb_pool* p, const void* d_action, void* stream) {
+  if (!p) return fail(EPB_ERR_INVALID, "null pool");
+  if (!p->x_attached) return fail(EPB_ERR_STATE, "exchange: peers not attached");
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
+  const int64_t half = (int64_t)(p->x_steps & 1) * p->x_world * p->slab_bytes;
+  const int64_t mine = half + (int64_t)p->x_rank * p->slab_bytes;
+  int rc = launch_batch(p, d_action, nullptr, p->N, d_action ? 0 : 1, p->x_base + mine, s);
+  if (rc != EPB_OK) return rc;
+  PeerView pv{};
+  pv.world = p->x_world;
+  pv.rank = p->x_rank;
+  for (int g = 0; g < p->x_world; ++g) {
+    pv.slice[g] = p->x_peer[g] + mine;
+    pv.flag[g] = reinterpret_cast<unsigned long long*>(p->x_peer[g] + p->x_flags_off) + p->x_rank;
+  }
+  const int64_t n16 = p->slab_bytes / 16;
+  int64_t blocks = (n16 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  push_kernel<<<(unsigned)blocks, 256, 0, s>>>(
+      pv, n16, reinterpret_cast<ExchangeCtl*>(p->x_base + p->x_ctl_off));
+  EPB_CUDA(cudaGetLastError());
+  ++p->launches;
+  ++p->x_steps;
+  return EPB_OK;
+}
+int epb_exchange_wait(epb_pool* p, void* stream, void** d_gathered) {
+  if (!p) return fail(EPB_ERR_INVALID, "null pool");
+  if (!p->x_attached || p->x_steps == 0)
+    return fail(EPB_ERR_STATE, "exchange: nothing has been exchanged yet");
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
+  wait_kernel<<<1, 32, 0, s>>>(
+      reinterpret_cast<const unsigned long long*>(p->x_base + p->x_flags_off), p->x_world,
+      reinterpret_cast<ExchangeCtl*>(p->x_base + p->x_ctl_off));
+  EPB_CUDA(cudaGetLastError());
+  ++p->launches;
+  if (d_gathered)
+    *d_gathered = p->x_base + (int64_t)((p->x_steps - 1) & 1) * p->x_world * p->slab_bytes;
+  return EPB_OK;
+}
+int epb_exchange_status(epb_pool* p, int64_t* steps_pushed, int* timed_out) {
+  if (!p) return fail(EPB_ERR_INVALID, "null pool");
+  if (!p->x_base) return fail(EPB_ERR_STATE, "exchange not initialised");
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
+  ExchangeCtl c{};
+  EPB_CUDA(cudaMemcpy(&c, p->x_base + p->x_ctl_off, sizeof(c), cudaMemcpyDeviceToHost));
+  if (steps_pushed) *steps_pushed = (int64_t)c.seq;
+  if (timed_out) *timed_out = c.error;
   return EPB_OK;
 }
 

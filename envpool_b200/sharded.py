@@ -4,12 +4,19 @@ The batched step path shards naturally: envs are independent (own mt19937, own s
 rank r of G owns the contiguous global ids [offset, offset + count) and seeds them with
 `seed + global_env_id` exactly as a single pool would (envpool/core/env.h:101-111) -- results
 do not depend on G.  The one exchange step of the path is an all-gather of the output
-columns, which reassembles the full `[num_envs, ...]` batch on every rank over NCCL /
-NVLink (gloo on CPU tensors in the host-logic tests).
+columns, which reassembles the full `[num_envs, ...]` batch on every rank.  Two transports:
+
+* the engine's own peer exchange (csrc/exchange.cuh): the step writes into this rank's slice
+  of a gather buffer that every peer maps through CUDA IPC, a push kernel stores the slice
+  into all peers over NVLink and raises sequence flags -- `enable_peer_exchange()`,
+  `reset_exchange()`, `step_exchange(actions)`;
+* `torch.distributed` all-gather (NCCL on GPUs; gloo on CPU tensors in the host-logic
+  tests) -- `all_gather()`; also the cross-check of the first.
 
     pool = ShardedPool("CartPole-v1", num_envs=1 << 20)         # inside torchrun
-    out = pool.reset_device(); full = pool.all_gather()
-    out = pool.step_device(local_actions); full = pool.all_gather()
+    pool.enable_peer_exchange()
+    full = pool.reset_exchange()                # {key: [world, n_local, ...]} on every rank
+    full = pool.step_exchange(local_actions)
 """
 from __future__ import annotations
 
@@ -150,3 +157,38 @@ class ShardedPool:
             self._full_slab = all_gather_packed(slab, getattr(self, "_full_slab", None),
                                                 self.group)
         return packed_views(self._full_slab, self.pool.keys, self.count)
+
+    # ------------------------------------------------------------------ peer exchange
+    def enable_peer_exchange(self):
+        """Allocate this rank's gather buffer and map every peer's (CUDA IPC handles travel
+        through `all_gather_object`).  Collective: every rank must call it."""
+        import torch.distributed as dist
+
+        handle = self.pool.exchange_init(self.world, self.rank)
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle, group=self.group)
+            self.pool.exchange_attach_ipc(handles)
+            dist.barrier(group=self.group)
+        self._peer = True
+
+    def _gathered(self):
+        import torch
+
+        from ._capi import _torch_view
+
+        ptr = self.pool.exchange_wait()
+        full = _torch_view(ptr, (self.world, self.pool.slab_bytes), torch.uint8,
+                           self.pool.device)
+        return packed_views(full, self.pool.keys, self.count)
+
+    def reset_exchange(self):
+        """Forced reset of all local envs + exchange; views valid until the second-next call."""
+        self.pool.step_exchange(None)
+        return self._gathered()
+
+    def step_exchange(self, local_actions):
+        """Step the local envs and hand back the gathered batch of ALL ranks as
+        `[world, n_local, ...]` views (enqueued on the pool stream, like step_device)."""
+        self.pool.step_exchange(local_actions)
+        return self._gathered()

@@ -1,0 +1,105 @@
+"""GPU: the peer exchange (include/envpool_b200.h "peer exchange", csrc/exchange.cuh) on ONE
+device -- two pools play rank 0 and rank 1 of a 2-way env-id sharding, attached to each
+other's gather buffers by raw pointer, each on its own stream.  After every step both
+ranks must hold the oracle's full batch (integer envs bit-exact).  The multi-process /
+CUDA-IPC flavour of the same path is tests/test_gpu_sharded.py (needs 2 GPUs)."""
+import numpy as np
+import pytest
+
+from helpers import assert_batch_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _views(pool, ptr, world, n_local):
+    import torch
+
+    from envpool_b200._capi import _torch_view
+    from envpool_b200.sharded import packed_views
+
+    full = _torch_view(ptr, (world, pool.slab_bytes), torch.uint8, pool.device)
+    return packed_views(full, pool.keys, n_local)
+
+
+@pytest.mark.parametrize("task,kw,n_act", [
+    ("FrozenLake", dict(max_episode_steps=100, iopt=4), 4),
+    ("CartPole", dict(max_episode_steps=200), 2),
+    ("Catch", dict(), 3),
+])
+def test_two_ranks_one_device(task, kw, n_act):
+    import torch
+
+    from envpool_b200._capi import CPool
+    from oracle.oracle_lib import OraclePool
+
+    n, world = 1000, 2          # not a multiple of the CTA size: exercises the padded tail
+    pools = [CPool(task, n, seed=3, env_id_offset=r * n, **kw) for r in range(world)]
+    orc = OraclePool(task, world * n, seed=3, **kw)
+    for r, p in enumerate(pools):
+        assert len(p.exchange_init(world, r)) == 64
+    bases = [p.exchange_base() for p in pools]
+    for p in pools:
+        p.exchange_attach(bases)
+    rng = np.random.default_rng(1)
+    want = orc.reset()
+    acts = None
+    for t in range(40):
+        d_acts = None if acts is None else [
+            torch.from_numpy(acts[r * n:(r + 1) * n].copy()).cuda() for r in range(world)]
+        torch.cuda.synchronize()
+        for r, p in enumerate(pools):          # all pushes are enqueued before any wait
+            p.step_exchange(None if d_acts is None else d_acts[r])
+        ptrs = [p.exchange_wait() for p in pools]
+        for p in pools:
+            p.sync()
+        for r, p in enumerate(pools):
+            got = {k: v.reshape((world * n,) + tuple(v.shape[2:])).cpu().numpy()
+                   for k, v in _views(p, ptrs[r], world, n).items()}
+            assert_batch_equal(got, want, task, 1e-5 if task == "CartPole" else 0.0,
+                               f"{task} rank {r} step {t}")
+        acts = rng.integers(0, n_act, size=world * n).astype(np.int32)
+        want = orc.step(acts)
+    for p in pools:
+        steps, timed_out = p.exchange_status()
+        assert steps == 40 and not timed_out
+        assert p.outputs_device_ptr() != 0
+    for p in pools:
+        p.close()
+
+
+def test_exchange_errors_and_single_rank():
+    import torch
+
+    from envpool_b200._capi import CPool, EpbError
+
+    p = CPool("NChain", 64, seed=0)
+    with pytest.raises(EpbError):
+        p.step_exchange(None)                  # not initialised
+    with pytest.raises(ValueError):
+        p.exchange_init(17, 0)                 # world out of range
+    with pytest.raises(ValueError):
+        p.exchange_init(2, 2)                  # rank out of range
+    p.exchange_init(2, 0)
+    with pytest.raises(EpbError):
+        p.exchange_init(2, 0)                  # twice
+    with pytest.raises(EpbError):
+        p.step_exchange(None)                  # peers not attached
+    p.close()
+
+    # world == 1 degenerates to a plain step into the gather buffer
+    q, ref = CPool("NChain", 64, seed=0), CPool("NChain", 64, seed=0)
+    q.exchange_init(1, 0)
+    with pytest.raises(EpbError):
+        q.exchange_wait()                      # nothing exchanged yet
+    a = torch.zeros(64, dtype=torch.int32, device="cuda")
+    for t in range(5):
+        q.step_exchange(None if t == 0 else a)
+        ptr = q.exchange_wait()
+        q.sync()
+        ref.reset_device() if t == 0 else ref.step_device(a)
+        ref.sync()
+        got = _views(q, ptr, 1, 64)
+        for k, v in ref.outputs_torch().items():
+            assert torch.equal(got[k][0], v), k
+    q.close()
+    ref.close()

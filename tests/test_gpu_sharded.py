@@ -1,6 +1,7 @@
 """GPU, 2 ranks (skipped on a single-GPU box): ShardedPool over NCCL -- each rank steps its
 env-id block, one all-gather of the packed outputs per step, and the gathered batch equals
-the oracle's full batch (toy_text: bit-exact)."""
+the oracle's full batch (toy_text: bit-exact); then the same through the engine's own peer
+exchange (CUDA IPC handles, NVLink stores, sequence flags)."""
 import os
 import socket
 import sys
@@ -41,6 +42,24 @@ def _worker(rank, world, port, ret):
         a = rng.integers(0, 4, size=n).astype(np.int32)
         pool.step_device(torch.from_numpy(a[pool.offset:pool.offset + pool.count]).cuda())
         want = orc.step(a)
+    # the engine's own peer exchange (CUDA IPC + NVLink stores) must agree with both
+    pool2 = ShardedPool("FrozenLake-v1", n, seed=5, device=rank)
+    orc2 = OraclePool("FrozenLake", n, seed=5, max_episode_steps=100, iopt=4)
+    pool2.enable_peer_exchange()
+    want = orc2.reset()
+    full = pool2.reset_exchange()
+    for t in range(25):
+        pool2.pool.sync()
+        for k, w in want.items():
+            g = full[k].reshape((n,) + tuple(full[k].shape[2:])).cpu().numpy()
+            ok &= bool(np.array_equal(g, w))
+        a = rng.integers(0, 4, size=n).astype(np.int32)
+        full = pool2.step_exchange(
+            torch.from_numpy(a[pool2.offset:pool2.offset + pool2.count]).cuda())
+        want = orc2.step(a)
+    pool2.pool.sync()
+    steps, timed_out = pool2.pool.exchange_status()
+    ok &= (steps == 26) and not timed_out
     ret[rank] = ok
     dist.barrier()
     dist.destroy_process_group()
