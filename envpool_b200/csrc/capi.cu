@@ -16,7 +16,6 @@
 
 #include "../../include/envpool_b200.h"
 #include "common.cuh"
-#include "exchange.cuh"
 #include "mujoco.cuh"
 
 namespace epb {
@@ -142,7 +141,17 @@ struct epb_pool {
   char* x_peer[kMaxPeers] = {};
   bool x_ipc[kMaxPeers] = {};
   bool x_attached = false;
+  bool x_fused = false;  // peer stores issued by the step kernel's epilogue (else push_kernel)
   uint64_t x_steps = 0;  // host count of exchanged steps; parity picks the gather half
+
+  int64_t x_mine(int parity) const {
+    return ((int64_t)parity * x_world + x_rank) * slab_bytes;
+  }
+  ExchangeCtl* x_ctl() const { return reinterpret_cast<ExchangeCtl*>(x_base + x_ctl_off); }
+  // the two per-parity PeerViews live behind the control block, in device memory
+  PeerView* x_view(int parity) const {
+    return reinterpret_cast<PeerView*>(x_base + x_ctl_off + 256) + parity;
+  }
 
   OutView slab_view(char* base) const {
     OutView ov{};
@@ -264,9 +273,66 @@ int get_event(epb_pool* p, cudaEvent_t* ev) {
   return EPB_OK;
 }
 
+// Copy n16 16-byte units of the local slice to every peer, then publish.
+__global__ void __launch_bounds__(256)
+push_kernel(const PeerView* __restrict__ pv, int64_t n16) {
+  const int world = pv->world, rank = pv->rank;
+  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(pv->slice[rank]);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    uint4 v = src[i];
+#pragma unroll 1
+    for (int g = 0; g < world; ++g)
+      if (g != rank) reinterpret_cast<uint4*>(pv->slice[g])[i] = v;
+  }
+  peer_publish(pv);
+}
+
+// One warp: lane g waits until rank g's slice of step `ctl->seq` has landed here.
+// Bounded: ~4e9 cycles (about 2 s) without progress sets ctl->error instead of hanging.
+__global__ void wait_kernel(const unsigned long long* flags, int world, ExchangeCtl* ctl) {
+  const unsigned long long want = ctl->seq;
+  if ((int)threadIdx.x < world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flags + threadIdx.x) < want) {
+      if (clock64() - t0 > 4000000000LL) {
+        atomicExch(&ctl->error, 1);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+}
+
+// Build the two per-parity PeerViews from the attached peer bases and copy them to the device.
+int upload_views(epb_pool* p) {
+  PeerView v[2];
+  memset(v, 0, sizeof(v));
+  for (int parity = 0; parity < 2; ++parity) {
+    PeerView& pv = v[parity];
+    pv.world = p->x_world;
+    pv.rank = p->x_rank;
+    pv.ctl = p->x_ctl();
+    for (int g = 0; g < p->x_world; ++g) {
+      pv.slice[g] = p->x_peer[g] + p->x_mine(parity);
+      pv.flag[g] =
+          reinterpret_cast<unsigned long long*>(p->x_peer[g] + p->x_flags_off) + p->x_rank;
+    }
+    pv.ncols = (int)p->keys.size();
+    for (int k = 0; k < pv.ncols; ++k) {
+      pv.col_rb[k] = p->keys[k].row_bytes;
+      pv.col_off[k] = p->keys[k].off;
+    }
+  }
+  EPB_CUDA(cudaMemcpy(p->x_view(0), v, sizeof(v), cudaMemcpyHostToDevice));
+  p->x_attached = true;
+  return EPB_OK;
+}
+
 // Launch one batch step on `stream`.  d_action/d_ids are device pointers.
 int launch_batch(epb_pool* p, const void* d_action, const int32_t* d_ids, int n,
-                 int force_reset, char* d_slab, cudaStream_t stream) {
+                 int force_reset, char* d_slab, cudaStream_t stream,
+                 const PeerView* peers = nullptr) {
   p->d_last = d_slab;
   if (p->kind == EPB_HALF_CHEETAH) {
     EPB_CUDA(mjc_launch_step(p->mjc, p->sv, p->slab_view(d_slab),
@@ -283,6 +349,7 @@ int launch_batch(epb_pool* p, const void* d_action, const int32_t* d_ids, int n,
   a.n = n;
   a.force_reset = force_reset;
   a.stream = stream;
+  a.peers = peers;
   EPB_CUDA(p->step_fn(a));
   ++p->launches;
   return EPB_OK;
@@ -788,14 +855,20 @@ int epb_exchange_init(epb_pool* p, int world, int rank, void* ipc_handle_out) {
   EPB_CUDA(guard.status);
   p->x_flags_off = 2 * (int64_t)world * p->slab_bytes;
   p->x_ctl_off = p->x_flags_off + 256;
-  p->x_bytes = p->x_ctl_off + 256;
+  p->x_bytes = p->x_ctl_off + 256 + ((2 * (int64_t)sizeof(PeerView) + 255) / 256) * 256;
   EPB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->x_base), (size_t)p->x_bytes));
   EPB_CUDA(cudaMemset(p->x_base, 0, (size_t)p->x_bytes));
   EPB_CUDA(cudaDeviceSynchronize());
   p->x_world = world;
   p->x_rank = rank;
   p->x_peer[rank] = p->x_base;
-  p->x_attached = (world == 1);
+  // HalfCheetah's kernels have no forwarding epilogue; ENVPOOL_B200_EXCHANGE=push is the A/B switch
+  const char* mode = getenv("ENVPOOL_B200_EXCHANGE");
+  p->x_fused = p->kind != EPB_HALF_CHEETAH && !(mode && strcmp(mode, "push") == 0);
+  if (world == 1) {
+    int rc = upload_views(p);
+    if (rc != EPB_OK) return rc;
+  }
   if (ipc_handle_out) {
     cudaIpcMemHandle_t h;
     EPB_CUDA(cudaIpcGetMemHandle(&h, p->x_base));
@@ -818,8 +891,9 @@ int epb_exchange_attach(epb_pool* p, void* const* peer_bases) {
     if (!peer_bases[g]) return fail(EPB_ERR_INVALID, "exchange: null peer base");
     p->x_peer[g] = static_cast<char*>(peer_bases[g]);
   }
-  p->x_attached = true;
-  return EPB_OK;
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
+  return upload_views(p);
 }
 int epb_exchange_attach_ipc(epb_pool* p, const void* ipc_handles) {
   if (!p || !ipc_handles) return fail(EPB_ERR_INVALID, "null argument");
@@ -835,8 +909,7 @@ int epb_exchange_attach_ipc(epb_pool* p, const void* ipc_handles) {
     p->x_peer[g] = static_cast<char*>(ptr);
     p->x_ipc[g] = true;
   }
-  p->x_attached = true;
-  return EPB_OK;
+  return upload_views(p);
 }
 int epb_step_exchange_device(epb_pool* p, const void* d_action, void* stream) {
   if (!p) return fail(EPB_ERR_INVALID, "null pool");
@@ -844,25 +917,23 @@ int epb_step_exchange_device(epb_pool* p, const void* d_action, void* stream) {
   DeviceGuard guard(p->cfg.device);
   EPB_CUDA(guard.status);
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
-  const int64_t half = (int64_t)(p->x_steps & 1) * p->x_world * p->slab_bytes;
-  const int64_t mine = half + (int64_t)p->x_rank * p->slab_bytes;
-  int rc = launch_batch(p, d_action, nullptr, p->N, d_action ? 0 : 1, p->x_base + mine, s);
-  if (rc != EPB_OK) return rc;
-  PeerView pv{};
-  pv.world = p->x_world;
-  pv.rank = p->x_rank;
-  for (int g = 0; g < p->x_world; ++g) {
-    pv.slice[g] = p->x_peer[g] + mine;
-    pv.flag[g] = reinterpret_cast<unsigned long long*>(p->x_peer[g] + p->x_flags_off) + p->x_rank;
+  const int parity = (int)(p->x_steps & 1);
+  char* mine = p->x_base + p->x_mine(parity);
+  const int force = d_action ? 0 : 1;
+  if (p->x_fused) {
+    int rc = launch_batch(p, d_action, nullptr, p->N, force, mine, s, p->x_view(parity));
+    if (rc != EPB_OK) return rc;
+  } else {
+    int rc = launch_batch(p, d_action, nullptr, p->N, force, mine, s);
+    if (rc != EPB_OK) return rc;
+    const int64_t n16 = p->slab_bytes / 16;
+    int64_t blocks = (n16 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    push_kernel<<<(unsigned)blocks, 256, 0, s>>>(p->x_view(parity), n16);
+    EPB_CUDA(cudaGetLastError());
+    ++p->launches;
   }
-  const int64_t n16 = p->slab_bytes / 16;
-  int64_t blocks = (n16 + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
-  push_kernel<<<(unsigned)blocks, 256, 0, s>>>(
-      pv, n16, reinterpret_cast<ExchangeCtl*>(p->x_base + p->x_ctl_off));
-  EPB_CUDA(cudaGetLastError());
-  ++p->launches;
   ++p->x_steps;
   return EPB_OK;
 }
@@ -875,7 +946,7 @@ int epb_exchange_wait(epb_pool* p, void* stream, void** d_gathered) {
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
   wait_kernel<<<1, 32, 0, s>>>(
       reinterpret_cast<const unsigned long long*>(p->x_base + p->x_flags_off), p->x_world,
-      reinterpret_cast<ExchangeCtl*>(p->x_base + p->x_ctl_off));
+      p->x_ctl());
   EPB_CUDA(cudaGetLastError());
   ++p->launches;
   if (d_gathered)

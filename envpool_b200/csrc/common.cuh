@@ -14,6 +14,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "exchange.cuh"
+
 namespace epb {
 
 constexpr int kMtN = 624;
@@ -364,7 +366,8 @@ __device__ __forceinline__ void pin_value(double& v) { asm volatile("" : "+d"(v)
 template <class Env, int kB = kBlock>
 __global__ void __launch_bounds__(kB)
 step_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ action,
-            const int32_t* __restrict__ env_ids, int n, int force_reset) {
+            const int32_t* __restrict__ env_ids, int n, int force_reset,
+            const PeerView* __restrict__ peers) {
   int row = blockIdx.x * kB + threadIdx.x;
   bool active = row < n;
   typename Env::State s;
@@ -402,6 +405,8 @@ step_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ acti
   } else if (active) {
     Env::write_obs(sv, ov, row, s, so);
   }
+  // sharded pools: forward this CTA's output rows to every peer GPU (exchange.cuh)
+  if (peers) peer_forward_rows<kB>(peers, (int64_t)blockIdx.x * kB, n);
 }
 
 // Fused rollout: T sync steps of all N envs in one launch; state stays in registers, the
@@ -460,6 +465,7 @@ struct LaunchArgs {
   int force_reset;
   int T;  // rollout only
   cudaStream_t stream;
+  const PeerView* peers;  // device pointer; non-NULL = fused peer exchange epilogue
 };
 typedef cudaError_t (*launch_fn)(const LaunchArgs&);
 
@@ -503,7 +509,7 @@ cudaError_t launch_step_b(const LaunchArgs& a) {
   cfg.numAttrs = (pdl_enabled() && cap == cudaStreamCaptureStatusNone) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, step_kernel<Env, kB>, a.sv, a.ov,
                             static_cast<const typename Env::Act*>(a.action), a.env_ids, a.n,
-                            a.force_reset);
+                            a.force_reset, a.peers);
 }
 
 template <class Env>

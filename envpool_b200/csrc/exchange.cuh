@@ -7,10 +7,15 @@
 //
 // mapped into every peer (CUDA IPC between processes, plain pointers inside one process).
 // A step writes its packed output slab straight into gather[parity][rank] of the LOCAL
-// allocation (no staging copy); `push_kernel` then stores that slice into gather[parity][rank]
-// of every peer over NVLink (16-byte stores, one read of the L2-hot slice per peer set) and
-// publishes the step's sequence number in flags[rank] of every rank with a system-scope
-// release.  `wait_kernel` (one warp) acquires flags[0..world) >= seq before the consumer of
+// allocation (no staging copy) and the same bytes go into gather[parity][rank] of every peer
+// over NVLink with 16-byte stores, after which the step's sequence number is published in
+// flags[rank] of every rank with a system-scope release.  Two producers of the peer stores:
+//   * fused (classic_control / toy_text): the step kernel's own epilogue -- each CTA forwards
+//     the rows it has just written (`peer_forward_rows`), so the transfer rides inside the
+//     step launch and no second kernel sits on the critical path;
+//   * `push_kernel` (HalfCheetah, or ENVPOOL_B200_EXCHANGE=push): a copy kernel behind the
+//     step kernel (capi.cu).
+// `wait_kernel` (one warp, capi.cu) acquires flags[0..world) >= seq before the consumer of
 // the gathered batch runs.  The two parities make step t+1's stores land in the other half
 // while step t is still being consumed: a peer cannot start pushing step t+2 before it has
 // seen this rank's flag for t+1, which this rank raises only after (stream order) its consumer
@@ -27,12 +32,7 @@ namespace epb {
 
 constexpr int kMaxPeers = 16;
 
-struct PeerView {
-  char* slice[kMaxPeers];                // gather[parity][rank] in the allocation of rank g
-  unsigned long long* flag[kMaxPeers];   // &flags[rank] in the allocation of rank g
-  int world;
-  int rank;
-};
+constexpr int kMaxCols = 13;  // 8 common state keys + at most 5 env keys (OutView::env)
 
 struct ExchangeCtl {
   unsigned int blocks_done;
@@ -40,6 +40,18 @@ struct ExchangeCtl {
   unsigned long long seq;   // steps pushed by this rank
   int error;                // 1 = a wait timed out
   int pad2;
+};
+
+struct PeerView {
+  char* slice[kMaxPeers];                // gather[parity][rank] in the allocation of rank g
+  unsigned long long* flag[kMaxPeers];   // &flags[rank] in the allocation of rank g
+  ExchangeCtl* ctl;                      // this rank's control block
+  int world;
+  int rank;
+  // packed-slab columns (fused epilogue): byte offset in the slab and bytes per row
+  int ncols;
+  int col_rb[kMaxCols];
+  int64_t col_off[kMaxCols];
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -51,46 +63,52 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-// Copy n16 16-byte units of the local slice to every peer, then signal.
-__global__ void __launch_bounds__(256)
-push_kernel(PeerView pv, int64_t n16, ExchangeCtl* ctl) {
-  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(pv.slice[pv.rank]);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
-    uint4 v = src[i];
-#pragma unroll 1
-    for (int g = 0; g < pv.world; ++g)
-      if (g != pv.rank) reinterpret_cast<uint4*>(pv.slice[g])[i] = v;
-  }
-  // last-block-done: every block fences its peer stores at system scope before it counts
+// Last-block-done publication: every CTA fences its peer stores at system scope before it
+// counts itself; the CTA that completes the count bumps the sequence number and raises
+// flags[rank] on every rank.  Call with all threads of the CTA.
+__device__ __forceinline__ void peer_publish(const PeerView* __restrict__ pv) {
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    ExchangeCtl* ctl = pv->ctl;
     unsigned int ticket = atomicAdd(&ctl->blocks_done, 1u);
     if (ticket == gridDim.x - 1) {
       ctl->blocks_done = 0;
       unsigned long long s = ctl->seq + 1;
       ctl->seq = s;
       __threadfence_system();
-      for (int g = 0; g < pv.world; ++g) st_release_sys(pv.flag[g], s);
+      const int world = pv->world;
+      for (int g = 0; g < world; ++g) st_release_sys(pv->flag[g], s);
     }
   }
 }
 
-// One warp: lane g waits until rank g's slice of step `ctl->seq` has landed here.
-// Bounded: ~4e9 cycles (about 2 s) without progress sets ctl->error instead of hanging.
-__global__ void wait_kernel(const unsigned long long* flags, int world, ExchangeCtl* ctl) {
-  const unsigned long long want = ctl->seq;
-  if ((int)threadIdx.x < world) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys(flags + threadIdx.x) < want) {
-      if (clock64() - t0 > 4000000000LL) {
-        atomicExch(&ctl->error, 1);
-        break;
-      }
-      __nanosleep(64);
+// Fused epilogue of the step kernels: the CTA forwards the output rows [row0, row0 + kB)
+// it has just written into its local gather slice to every peer, column by column, then
+// publishes.  Requires identity row<->env mapping (sync step of all envs) and kB % 16 == 0,
+// so that every per-column chunk starts 16-byte aligned; the tail CTA may copy up to 15
+// bytes past its last row, which stays inside the column's 256-byte padding.
+template <int kB>
+__device__ __forceinline__ void peer_forward_rows(const PeerView* __restrict__ pv, int64_t row0,
+                                                  int n) {
+  static_assert(kB % 16 == 0, "CTA rows must keep 1-byte columns 16-byte aligned");
+  __syncthreads();  // all rows of this CTA are written (by this CTA)
+  const int64_t left = (int64_t)n - row0;
+  const int rows = left < kB ? (int)left : kB;
+  const int world = pv->world, rank = pv->rank, ncols = pv->ncols;
+  const char* local = pv->slice[rank];
+  for (int k = 0; k < ncols; ++k) {
+    const int rb = pv->col_rb[k];
+    const int64_t off = pv->col_off[k] + row0 * rb;
+    const int n16 = (rows * rb + 15) >> 4;
+    for (int i = threadIdx.x; i < n16; i += kB) {
+      const uint4 v = *reinterpret_cast<const uint4*>(local + off + 16 * (int64_t)i);
+#pragma unroll 1
+      for (int g = 0; g < world; ++g)
+        if (g != rank) *reinterpret_cast<uint4*>(pv->slice[g] + off + 16 * (int64_t)i) = v;
     }
   }
+  peer_publish(pv);
 }
 
 }  // namespace epb
