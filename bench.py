@@ -393,7 +393,7 @@ def run_peer_exchange(args, torch, dist, pool, actions, dev, world, rank):
     bad = torch.tensor([1 if timed_out else 0], device=dev, dtype=torch.int32)
     dist.all_reduce(bad, op=dist.ReduceOp.MAX)
     if bad.item():
-        return {"unavailable": "a peer wait hit its 2 s bound"}
+        return {"unavailable": "a peer wait hit its time bound"}
     dist.barrier()
     gathered = pool.slab_bytes * (world - 1)
     return {"value": pool.n * world * steps / (ms * 1e-3), "unit": "env-steps/s", "steps": steps,

@@ -141,6 +141,7 @@ struct epb_pool {
   char* x_peer[kMaxPeers] = {};
   bool x_ipc[kMaxPeers] = {};
   bool x_attached = false;
+  long long x_timeout_ns = 10000000000LL;
   bool x_fused = false;  // peer stores issued by the step kernel's epilogue (else push_kernel)
   uint64_t x_steps = 0;  // host count of exchanged steps; parity picks the gather half
 
@@ -289,13 +290,18 @@ push_kernel(const PeerView* __restrict__ pv, int64_t n16) {
 }
 
 // One warp: lane g waits until rank g's slice of step `ctl->seq` has landed here.
-// Bounded: ~4e9 cycles (about 2 s) without progress sets ctl->error instead of hanging.
-__global__ void wait_kernel(const unsigned long long* flags, int world, ExchangeCtl* ctl) {
+// Bounded: `timeout_ns` without progress (default 10 s, ENVPOOL_B200_EXCHANGE_TIMEOUT_S) sets
+// ctl->error instead of hanging the GPU when a peer has died.
+__global__ void wait_kernel(const unsigned long long* flags, int world, ExchangeCtl* ctl,
+                            long long timeout_ns) {
   const unsigned long long want = ctl->seq;
   if ((int)threadIdx.x < world) {
-    const long long t0 = clock64();
+    long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (ld_acquire_sys(flags + threadIdx.x) < want) {
-      if (clock64() - t0 > 4000000000LL) {
+      long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) {
         atomicExch(&ctl->error, 1);
         break;
       }
@@ -865,6 +871,10 @@ int epb_exchange_init(epb_pool* p, int world, int rank, void* ipc_handle_out) {
   // HalfCheetah's kernels have no forwarding epilogue; ENVPOOL_B200_EXCHANGE=push is the A/B switch
   const char* mode = getenv("ENVPOOL_B200_EXCHANGE");
   p->x_fused = p->kind != EPB_HALF_CHEETAH && !(mode && strcmp(mode, "push") == 0);
+  if (const char* to = getenv("ENVPOOL_B200_EXCHANGE_TIMEOUT_S")) {
+    double sec = atof(to);
+    if (sec > 0) p->x_timeout_ns = (long long)(sec * 1e9);
+  }
   if (world == 1) {
     int rc = upload_views(p);
     if (rc != EPB_OK) return rc;
@@ -946,7 +956,7 @@ int epb_exchange_wait(epb_pool* p, void* stream, void** d_gathered) {
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
   wait_kernel<<<1, 32, 0, s>>>(
       reinterpret_cast<const unsigned long long*>(p->x_base + p->x_flags_off), p->x_world,
-      p->x_ctl());
+      p->x_ctl(), p->x_timeout_ns);
   EPB_CUDA(cudaGetLastError());
   ++p->launches;
   if (d_gathered)

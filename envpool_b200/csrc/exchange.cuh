@@ -63,9 +63,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // Last-block-done publication: every CTA fences its peer stores at system scope before it
 // counts itself; the CTA that completes the count bumps the sequence number and raises
-// flags[rank] on every rank.  Call with all threads of the CTA.
+// flags[rank] on every rank -- ONE system fence, then relaxed flag stores (a release per
+// flag would pay one NVLink round trip per peer).  Call with all threads of the CTA.
 __device__ __forceinline__ void peer_publish(const PeerView* __restrict__ pv) {
   __threadfence_system();
   __syncthreads();
@@ -78,34 +83,70 @@ __device__ __forceinline__ void peer_publish(const PeerView* __restrict__ pv) {
       ctl->seq = s;
       __threadfence_system();
       const int world = pv->world;
-      for (int g = 0; g < world; ++g) st_release_sys(pv->flag[g], s);
+      for (int g = 0; g < world; ++g) st_relaxed_sys(pv->flag[g], s);
     }
   }
 }
 
 // Fused epilogue of the step kernels: the CTA forwards the output rows [row0, row0 + kB)
-// it has just written into its local gather slice to every peer, column by column, then
-// publishes.  Requires identity row<->env mapping (sync step of all envs) and kB % 16 == 0,
-// so that every per-column chunk starts 16-byte aligned; the tail CTA may copy up to 15
-// bytes past its last row, which stays inside the column's 256-byte padding.
+// it has just written into its local gather slice to every peer, then publishes.  The rows
+// of all columns are treated as one list of 16-byte units (column k contributes
+// ceil(rows * row_bytes / 16) of them); each thread loads up to four units before it issues
+// any peer store, so the L2 read latency is paid once, not once per column.  Requires the
+// identity row<->env mapping (sync step of all envs) and kB % 16 == 0, so that every
+// per-column chunk starts 16-byte aligned; the tail CTA may copy up to 15 bytes past its
+// last row, which stays inside the column's 256-byte padding.
 template <int kB>
 __device__ __forceinline__ void peer_forward_rows(const PeerView* __restrict__ pv, int64_t row0,
                                                   int n) {
   static_assert(kB % 16 == 0, "CTA rows must keep 1-byte columns 16-byte aligned");
-  __syncthreads();  // all rows of this CTA are written (by this CTA)
+  __shared__ int s_first[kMaxCols + 1];   // first unit of column k in this CTA's unit list
+  __shared__ int64_t s_off[kMaxCols];     // slab byte offset of this CTA's rows in column k
+  __shared__ char* s_peer[kMaxPeers];
   const int64_t left = (int64_t)n - row0;
   const int rows = left < kB ? (int)left : kB;
   const int world = pv->world, rank = pv->rank, ncols = pv->ncols;
-  const char* local = pv->slice[rank];
-  for (int k = 0; k < ncols; ++k) {
-    const int rb = pv->col_rb[k];
-    const int64_t off = pv->col_off[k] + row0 * rb;
-    const int n16 = (rows * rb + 15) >> 4;
-    for (int i = threadIdx.x; i < n16; i += kB) {
-      const uint4 v = *reinterpret_cast<const uint4*>(local + off + 16 * (int64_t)i);
+  const int tid = threadIdx.x;
+  if (tid < ncols) {
+    const int rb = pv->col_rb[tid];
+    s_first[tid + 1] = (rows * rb + 15) >> 4;
+    s_off[tid] = pv->col_off[tid] + row0 * rb;
+  }
+  if (tid < world) s_peer[tid] = pv->slice[tid];
+  __syncthreads();  // tables ready; all rows of this CTA are written (by this CTA)
+  if (tid == 0) {
+    int acc = 0;
+    s_first[0] = 0;
+    for (int k = 0; k < ncols; ++k) {
+      acc += s_first[k + 1];
+      s_first[k + 1] = acc;
+    }
+  }
+  __syncthreads();
+  const int total = s_first[ncols];
+  const char* local = s_peer[rank];
+  constexpr int kU = 4;
+  for (int u0 = tid; u0 < total; u0 += kU * kB) {
+    uint4 v[kU];
+    int64_t off[kU];
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      const int u = u0 + j * kB;
+      off[j] = -1;
+      if (u < total) {
+        int k = 0;
+        while (u >= s_first[k + 1]) ++k;
+        off[j] = s_off[k] + 16 * (int64_t)(u - s_first[k]);
+        v[j] = *reinterpret_cast<const uint4*>(local + off[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      if (off[j] >= 0) {
 #pragma unroll 1
-      for (int g = 0; g < world; ++g)
-        if (g != rank) *reinterpret_cast<uint4*>(pv->slice[g] + off + 16 * (int64_t)i) = v;
+        for (int g = 0; g < world; ++g)
+          if (g != rank) *reinterpret_cast<uint4*>(s_peer[g] + off[j]) = v[j];
+      }
     }
   }
   peer_publish(pv);
