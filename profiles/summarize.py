@@ -124,6 +124,29 @@ def main():
         if os.path.exists(st):
             lines.append(f"\n`pytest tests/test_gpu_sharded.py` on this box: "
                          f"`{open(st).read().strip().splitlines()[-1]}`")
+    # engine peer exchange vs NCCL (tracked raw lines; runs of profiles/run_exchange8.sh and
+    # the 2-GPU equivalents)
+    for g in (2, 8):
+        xp = os.path.join(DST, f"r1_bench_lines_{g}gpu_exchange.jsonl")
+        if not os.path.exists(xp):
+            continue
+        lines.append(f"\n## {g} x B200: the engine's NVLink peer exchange (`csrc/exchange.cuh`) vs one "
+                     f"NCCL all-gather per step (`profiles/r1_bench_lines_{g}gpu_exchange.jsonl`)\n")
+        lines.append("| workload | step only us | + engine exchange us (G env-steps/s, NVLink GB/s in "
+                     "per GPU) | + NCCL all-gather us (G/s, GB/s) | exchange producer |")
+        lines.append("|---|---|---|---|---|")
+        for ln in open(xp):
+            d = json.loads(ln)
+            px, nc = d.get("with_allgather") or {}, d.get("with_allgather_nccl") or {}
+            if "value" not in px:
+                continue
+            prod = "push kernel" if ("HalfCheetah" in d["config"]["workload"]
+                                     or "push" in d.get("file", "")) else "fused step-kernel epilogue"
+            cell = lambda a: "-" if "value" not in a else "{} ({}, {})".format(
+                fmt(a["ms_per_step"] * 1e3, 1), fmt(a["value"] / 1e9, 3),
+                fmt(a["nvlink_gbs_in_per_gpu"], 0))
+            lines.append("| {} | {} | {} | {} | {} |".format(
+                d["config"]["workload"], fmt(d["ms_per_step"] * 1e3, 1), cell(px), cell(nc), prod))
     traffic = {}
     for rep, label, key in (("prof_step_cartpole65536", "step_kernel<CartPole<double>>, N=65536",
                              "CartPole-v1:65536:f64"),
