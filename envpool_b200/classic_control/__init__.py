@@ -1,28 +1,16 @@
-"""Classic control env in envpool_b200 (mirror of envpool/classic_control/__init__.py)."""
+"""classic_control family: binds the engine's pybind11 classes (`_XxxEnvSpec` / `_XxxEnvPool`, csrc/py_module.cc)
+to the Python adapters and exports, per env, `XxxEnvSpec`, `XxxDMEnvPool` and
+`XxxGymnasiumEnvPool` -- the names envpool/classic_control/__init__.py exports, so that
+`registration.py` import paths stay interchangeable with the reference's."""
 from ..python.api import py_env
-from .classic_control_envpool import (_AcrobotEnvPool, _AcrobotEnvSpec, _CartPoleEnvPool,
-                                      _CartPoleEnvSpec, _MountainCarContinuousEnvPool,
-                                      _MountainCarContinuousEnvSpec, _MountainCarEnvPool,
-                                      _MountainCarEnvSpec, _PendulumEnvPool,
-                                      _PendulumEnvSpec)
+from . import classic_control_envpool as _ext
 
-CartPoleEnvSpec, CartPoleDMEnvPool, CartPoleGymnasiumEnvPool = py_env(
-    _CartPoleEnvSpec, _CartPoleEnvPool)
-PendulumEnvSpec, PendulumDMEnvPool, PendulumGymnasiumEnvPool = py_env(
-    _PendulumEnvSpec, _PendulumEnvPool)
-MountainCarEnvSpec, MountainCarDMEnvPool, MountainCarGymnasiumEnvPool = py_env(
-    _MountainCarEnvSpec, _MountainCarEnvPool)
-(MountainCarContinuousEnvSpec, MountainCarContinuousDMEnvPool,
- MountainCarContinuousGymnasiumEnvPool) = py_env(_MountainCarContinuousEnvSpec,
-                                                 _MountainCarContinuousEnvPool)
-AcrobotEnvSpec, AcrobotDMEnvPool, AcrobotGymnasiumEnvPool = py_env(
-    _AcrobotEnvSpec, _AcrobotEnvPool)
+ENVS = ("CartPole", "Pendulum", "MountainCar", "MountainCarContinuous", "Acrobot")
 
-__all__ = [
-    "CartPoleEnvSpec", "CartPoleDMEnvPool", "CartPoleGymnasiumEnvPool",
-    "PendulumEnvSpec", "PendulumDMEnvPool", "PendulumGymnasiumEnvPool",
-    "MountainCarEnvSpec", "MountainCarDMEnvPool", "MountainCarGymnasiumEnvPool",
-    "MountainCarContinuousEnvSpec", "MountainCarContinuousDMEnvPool",
-    "MountainCarContinuousGymnasiumEnvPool",
-    "AcrobotEnvSpec", "AcrobotDMEnvPool", "AcrobotGymnasiumEnvPool",
-]
+__all__ = []
+for _env in ENVS:
+    _classes = py_env(getattr(_ext, f"_{_env}EnvSpec"), getattr(_ext, f"_{_env}EnvPool"))
+    for _suffix, _cls in zip(("EnvSpec", "DMEnvPool", "GymnasiumEnvPool"), _classes):
+        globals()[_env + _suffix] = _cls
+        __all__.append(_env + _suffix)
+del _env, _classes, _suffix, _cls

@@ -1,10 +1,16 @@
-"""MuJoCo gym env in envpool_b200: HalfCheetah, the MuJoCo task on the accelerated path
-(mirror of envpool/mujoco/gym/__init__.py for that task)."""
+"""mujoco/gym family (HalfCheetah, the MuJoCo task on the accelerated path): binds the engine's pybind11 classes (`_XxxEnvSpec` / `_XxxEnvPool`, csrc/py_module.cc)
+to the Python adapters and exports, per env, `XxxEnvSpec`, `XxxDMEnvPool` and
+`XxxGymnasiumEnvPool` -- the names envpool/mujoco/gym/__init__.py exports, so that
+`registration.py` import paths stay interchangeable with the reference's."""
 from ...python.api import py_env
-from ..mujoco_gym_envpool import _GymHalfCheetahEnvPool, _GymHalfCheetahEnvSpec
+from .. import mujoco_gym_envpool as _ext
 
-(GymHalfCheetahEnvSpec, GymHalfCheetahDMEnvPool,
- GymHalfCheetahGymnasiumEnvPool) = py_env(_GymHalfCheetahEnvSpec, _GymHalfCheetahEnvPool)
+ENVS = ("GymHalfCheetah",)
 
-__all__ = ["GymHalfCheetahEnvSpec", "GymHalfCheetahDMEnvPool",
-           "GymHalfCheetahGymnasiumEnvPool"]
+__all__ = []
+for _env in ENVS:
+    _classes = py_env(getattr(_ext, f"_{_env}EnvSpec"), getattr(_ext, f"_{_env}EnvPool"))
+    for _suffix, _cls in zip(("EnvSpec", "DMEnvPool", "GymnasiumEnvPool"), _classes):
+        globals()[_env + _suffix] = _cls
+        __all__.append(_env + _suffix)
+del _env, _classes, _suffix, _cls

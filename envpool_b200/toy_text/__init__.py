@@ -1,25 +1,16 @@
-"""Toy text env in envpool_b200 (mirror of envpool/toy_text/__init__.py)."""
+"""toy_text family: binds the engine's pybind11 classes (`_XxxEnvSpec` / `_XxxEnvPool`, csrc/py_module.cc)
+to the Python adapters and exports, per env, `XxxEnvSpec`, `XxxDMEnvPool` and
+`XxxGymnasiumEnvPool` -- the names envpool/toy_text/__init__.py exports, so that
+`registration.py` import paths stay interchangeable with the reference's."""
 from ..python.api import py_env
-from .toy_text_envpool import (_BlackjackEnvPool, _BlackjackEnvSpec, _CatchEnvPool,
-                               _CatchEnvSpec, _CliffWalkingEnvPool, _CliffWalkingEnvSpec,
-                               _FrozenLakeEnvPool, _FrozenLakeEnvSpec, _NChainEnvPool,
-                               _NChainEnvSpec, _TaxiEnvPool, _TaxiEnvSpec)
+from . import toy_text_envpool as _ext
 
-CatchEnvSpec, CatchDMEnvPool, CatchGymnasiumEnvPool = py_env(_CatchEnvSpec, _CatchEnvPool)
-FrozenLakeEnvSpec, FrozenLakeDMEnvPool, FrozenLakeGymnasiumEnvPool = py_env(
-    _FrozenLakeEnvSpec, _FrozenLakeEnvPool)
-TaxiEnvSpec, TaxiDMEnvPool, TaxiGymnasiumEnvPool = py_env(_TaxiEnvSpec, _TaxiEnvPool)
-NChainEnvSpec, NChainDMEnvPool, NChainGymnasiumEnvPool = py_env(_NChainEnvSpec, _NChainEnvPool)
-CliffWalkingEnvSpec, CliffWalkingDMEnvPool, CliffWalkingGymnasiumEnvPool = py_env(
-    _CliffWalkingEnvSpec, _CliffWalkingEnvPool)
-BlackjackEnvSpec, BlackjackDMEnvPool, BlackjackGymnasiumEnvPool = py_env(
-    _BlackjackEnvSpec, _BlackjackEnvPool)
+ENVS = ("Catch", "FrozenLake", "Taxi", "NChain", "CliffWalking", "Blackjack")
 
-__all__ = [
-    "CatchEnvSpec", "CatchDMEnvPool", "CatchGymnasiumEnvPool",
-    "FrozenLakeEnvSpec", "FrozenLakeDMEnvPool", "FrozenLakeGymnasiumEnvPool",
-    "TaxiEnvSpec", "TaxiDMEnvPool", "TaxiGymnasiumEnvPool",
-    "NChainEnvSpec", "NChainDMEnvPool", "NChainGymnasiumEnvPool",
-    "CliffWalkingEnvSpec", "CliffWalkingDMEnvPool", "CliffWalkingGymnasiumEnvPool",
-    "BlackjackEnvSpec", "BlackjackDMEnvPool", "BlackjackGymnasiumEnvPool",
-]
+__all__ = []
+for _env in ENVS:
+    _classes = py_env(getattr(_ext, f"_{_env}EnvSpec"), getattr(_ext, f"_{_env}EnvPool"))
+    for _suffix, _cls in zip(("EnvSpec", "DMEnvPool", "GymnasiumEnvPool"), _classes):
+        globals()[_env + _suffix] = _cls
+        __all__.append(_env + _suffix)
+del _env, _classes, _suffix, _cls

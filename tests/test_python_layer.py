@@ -71,3 +71,29 @@ def test_tree_helpers():
     d = to_namedtuple("State", fill_tree(dm_structure("State", keys), vals))
     assert d.State.obs == 8 and d.State.players.env_id == 1 and d.State.state == 9
     assert d.step_type == 6
+
+
+def test_adapter_folds_without_a_device(engine_built):
+    """The dm / gymnasium adapters fold the flat `_recv()` column list (state-key order)
+    into TimeStep / the gymnasium 5-tuple; the fold needs no engine instance."""
+    from envpool_b200.classic_control import CartPoleDMEnvPool, CartPoleGymnasiumEnvPool
+
+    assert CartPoleGymnasiumEnvPool._state_keys == [
+        "info:env_id", "info:players.env_id", "elapsed_step", "done", "reward", "discount",
+        "step_type", "trunc", "obs"]
+    n = 3
+    ids = np.arange(n, dtype=np.int32)
+    done, trunc = np.array([0, 1, 1], bool), np.array([0, 0, 1], bool)
+    obs = np.arange(4 * n, dtype=np.float32).reshape(n, 4)
+    cols = [ids, ids, np.full(n, 7, np.int32), done, np.ones(n, np.float32),
+            (~done).astype(np.float32), np.array([1, 2, 2], np.int32), trunc, obs]
+    o, info = CartPoleGymnasiumEnvPool._to(None, cols, True, True)
+    assert o is obs and info["env_id"] is ids and info["players"]["env_id"] is ids
+    assert (info["elapsed_step"] == 7).all()
+    o, rew, term, tr, info = CartPoleGymnasiumEnvPool._to(None, cols, False, True)
+    assert term.tolist() == [False, True, False] and tr.tolist() == [False, False, True]
+    ts = CartPoleDMEnvPool._to(None, cols, False, True)
+    assert ts.observation.obs is obs and ts.observation.players.env_id is ids
+    assert ts.last().tolist() == [False, True, True] and ts.mid().tolist() == [True, False, False]
+    with pytest.raises(RuntimeError):
+        CartPoleDMEnvPool.xla(None)
