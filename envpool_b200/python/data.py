@@ -56,6 +56,15 @@ class Box:
         self.low = np.broadcast_to(np.asarray(low, dtype=self.dtype), self.shape).copy()
         self.high = np.broadcast_to(np.asarray(high, dtype=self.dtype), self.shape).copy()
 
+    # dm_env.specs.BoundedArray vocabulary (the same stand-in serves both adapters)
+    @property
+    def minimum(self):
+        return self.low
+
+    @property
+    def maximum(self):
+        return self.high
+
     def contains(self, x):
         x = np.asarray(x)
         return bool(x.shape == self.shape and np.all(x >= self.low) and np.all(x <= self.high))
@@ -70,6 +79,10 @@ class Discrete:
         self.start = int(start)
         self.shape = ()
         self.dtype = np.dtype(np.int64)
+
+    @property
+    def num_values(self):  # dm_env.specs.DiscreteArray vocabulary
+        return self.n
 
     def contains(self, x):
         return self.start <= int(x) < self.start + self.n
