@@ -692,7 +692,10 @@ int epb_recv_slab_ex(epb_pool* p, void** slab, int* row0, int* n_rows) {
   while (filled < want) {
     Pending& pd = p->pending.front();
     e = wait_head(pd);
-    if (e != cudaSuccess) return fail(EPB_ERR_CUDA, std::string("recv: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      p->free_slabs.push_back(dst);  // nothing leased yet: hand the assembly slab back
+      return fail(EPB_ERR_CUDA, std::string("recv: ") + cudaGetErrorString(e));
+    }
     int take = pd.n - pd.row0;
     if (take > want - filled) take = want - filled;
     for (const Key& k : p->keys)
