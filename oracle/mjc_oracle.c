@@ -616,6 +616,20 @@ static void forward(const mjc_model* m, mjc_data* d, double* M, double* qfrc_smo
                qfrc_constraint, &d->niter);
 }
 
+/* Diagnostics for tests/test_mjc_oracle.py: joint-space inertia M(q) (row-major NVxNV), bias
+ * force c(q, qvel) (Coriolis/centrifugal + gravity) and the gravitational potential
+ * V(q) = sum_b m_b |g| z_com,b -- enough to check the bias against Lagrange's equations,
+ * c_i = sum_jk (dM_ij/dq_k - 1/2 dM_jk/dq_i) v_j v_k + dV/dq_i, by finite differences. */
+double mjc_debug_dynamics(const mjc_model* m, const double* qpos, const double* qvel,
+                          double* M_out, double* bias_out) {
+  double org[NB][2], th[NB], com[NB][2], V = 0;
+  kinematics(m, qpos, org, th, com);
+  if (M_out) mass_matrix(m, org, com, M_out);
+  if (bias_out) bias_force(m, qvel, org, com, bias_out);
+  for (int b = 0; b < NB; ++b) V -= m->mass[b] * m->gravity * com[b][1]; /* gravity < 0 */
+  return V;
+}
+
 void mjc_forward(const mjc_model* m, mjc_data* d) {
   double M[NV * NV], fs[NV], fc[NV];
   forward(m, d, M, fs, fc);

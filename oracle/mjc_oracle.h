@@ -37,6 +37,10 @@ int mjc_nefc(const mjc_data* d);
  * returns the count */
 int mjc_model_constants(const mjc_model* m, double* out, int cap);
 
+/* M(q) [81], bias(q, qvel) [9] (either may be NULL); returns the gravitational potential */
+double mjc_debug_dynamics(const mjc_model* m, const double* qpos, const double* qvel,
+                          double* M_out, double* bias_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -184,6 +184,8 @@ class MjcSim:
         L.mjc_forward.argtypes = [vp, vp]
         L.mjc_nefc.argtypes = [vp]
         L.mjc_model_constants.argtypes = [vp, vp, ctypes.c_int]
+        L.mjc_debug_dynamics.restype = ctypes.c_double
+        L.mjc_debug_dynamics.argtypes = [vp, vp, vp, vp, vp]
         self.L = L
         self.m = L.mjc_make_half_cheetah()
         self.d = L.mjc_make_data(self.m)
@@ -215,6 +217,15 @@ class MjcSim:
     @property
     def nefc(self):
         return self.L.mjc_nefc(self.d)
+
+    def dynamics(self, qpos, qvel):
+        """(M [9,9], bias [9], gravitational potential) at an arbitrary (qpos, qvel)."""
+        q = np.ascontiguousarray(qpos, dtype=np.float64)
+        v = np.ascontiguousarray(qvel, dtype=np.float64)
+        M, c = np.zeros((9, 9)), np.zeros(9)
+        V = self.L.mjc_debug_dynamics(self.m, q.ctypes.data, v.ctypes.data, M.ctypes.data,
+                                      c.ctypes.data)
+        return M, c, V
 
     def constants(self):
         buf = np.zeros(64)

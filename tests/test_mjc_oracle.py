@@ -109,3 +109,38 @@ def test_env_reward_and_obs_algebra():
     assert s["done"].all() and s["trunc"].all()
     s = p.step(np.zeros((2, 6)))
     assert (s["elapsed_step"] == 0).all() and (s["reward"] == 0).all()
+
+
+def test_bias_force_satisfies_lagranges_equations(sim):
+    """Independent of MuJoCo's conventions: for T = 1/2 v^T M(q) v and V = sum m |g| z the bias
+    force of the restatement (computed from body accelerations, RNE style) must equal
+    c_i = sum_jk (dM_ij/dq_k - 1/2 dM_jk/dq_i) v_j v_k + dV/dq_i (central differences of the
+    restatement's own M and V).  Pins kinematics, Jacobians, inertia and the Coriolis /
+    centrifugal / gravity terms against each other; the soft-constraint model is what stays
+    unpinned."""
+    rng = np.random.default_rng(3)
+    eps = 1e-6
+    for _ in range(20):
+        q = rng.uniform(-0.6, 0.6, size=9)
+        v = rng.normal(0, 2.0, size=9)
+        M, c, _ = sim.dynamics(q, v)
+        np.testing.assert_allclose(M, M.T, rtol=0, atol=1e-12)
+        assert np.linalg.eigvalsh(M).min() > 0
+        dM = np.zeros((9, 9, 9))      # dM[k] = dM/dq_k
+        dV = np.zeros(9)
+        for k in range(9):
+            dq = np.zeros(9)
+            dq[k] = eps
+            Mp, _, Vp = sim.dynamics(q + dq, v)
+            Mm, _, Vm = sim.dynamics(q - dq, v)
+            dM[k] = (Mp - Mm) / (2 * eps)
+            dV[k] = (Vp - Vm) / (2 * eps)
+        want = np.einsum("kij,j,k->i", dM, v, v) - 0.5 * np.einsum("ijk,j,k->i", dM, v, v) + dV
+        np.testing.assert_allclose(c, want, rtol=0, atol=2e-6 * (1 + np.abs(want).max()))
+    # the inertia does not depend on the root translation, and momentum rows are plain sums
+    M0, _, _ = sim.dynamics(np.zeros(9), np.zeros(9))
+    M1, _, _ = sim.dynamics(np.r_[3.0, -1.0, np.zeros(7)], np.zeros(9))
+    np.testing.assert_allclose(M0, M1, rtol=0, atol=1e-12)
+    total = sim.constants()["mass"].sum()
+    assert abs(M0[0, 0] - total) < 1e-12 and abs(M0[1, 1] - total) < 1e-12
+    assert abs(M0[0, 1]) < 1e-12
