@@ -281,6 +281,7 @@ class PoolBase {
   std::vector<epb_key_info> keys;
   epb_key_info act{};
   std::vector<int32_t> env_seed;
+  int device_ordinal = 0;  // resolved CUDA device of the pool
 
   void Create(const SpecBase& spec, int device, const std::string& precision,
               int env_id_offset) {
@@ -345,6 +346,7 @@ class PoolBase {
     if (prec != "f64" && prec != "f32")
       throw std::invalid_argument("precision must be 'f64' or 'f32'");
     c.device = device;
+    device_ordinal = device;
     c.precision = prec == "f32" ? EPB_PREC_F32 : EPB_PREC_F64;
     c.env_id_offset = env_id_offset;
     h = std::make_shared<PoolHandle>();
@@ -421,6 +423,7 @@ class PoolBase {
   }
   py::tuple Xla() { throw std::runtime_error("XLA is not available in envpool_b200"); }
   std::uintptr_t Handle() const { return reinterpret_cast<std::uintptr_t>(h->p); }
+  int Device() const { return device_ordinal; }
 };
 
 // One distinct C++ type per env so pybind11 creates one distinct Python class each.
@@ -478,7 +481,8 @@ void register_env(py::module_& m, const EnvDesc* d) {
       .def("_render", &PyPool<K>::Render)
       .def("_xla", &PyPool<K>::Xla)
       // extension: raw epb_pool* for the device-resident C-ABI entry points
-      .def_property_readonly("_handle", &PyPool<K>::Handle);
+      .def_property_readonly("_handle", &PyPool<K>::Handle)
+      .def_property_readonly("_device", &PyPool<K>::Device);
   pool.attr("_state_keys") = state_keys;
   pool.attr("_action_keys") = action_keys;
 }

@@ -65,13 +65,14 @@ class EnvPoolMixin(ABC):
             if not hasattr(self, "_last_action_name"):
                 self._last_action_name = self._spec._action_keys[-1]
             if isinstance(action, np.ndarray):
-                action = action.astype(self._last_action_type, order="C")
+                # no copy when the caller already passes the spec dtype, C-contiguous
+                action = action.astype(self._last_action_type, order="C", copy=False)
             adict = {self._last_action_name: action}
         if env_id is None:
             if "env_id" not in adict:
                 adict["env_id"] = self.all_env_ids
         else:
-            adict["env_id"] = env_id.astype(np.int32)
+            adict["env_id"] = _normalize_env_id(env_id)
         if "players.env_id" not in adict:
             adict["players.env_id"] = _normalize_env_id(adict["env_id"])
         if not hasattr(self, "_action_names"):
@@ -144,7 +145,8 @@ class EnvPoolMixin(ABC):
         if not hasattr(self, "_device_pool"):
             from .._capi import CPool
 
-            self._device_pool = CPool.borrow(self._handle, self.config["num_envs"])
+            self._device_pool = CPool.borrow(self._handle, self.config["num_envs"],
+                                             device=self._device)
         return self._device_pool
 
     def step_device(self, action, env_id=None, stream=None):
