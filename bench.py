@@ -260,7 +260,9 @@ def run_ours(args):
         if rank == 0:
             result["e2e"] = e2e
     if rank == 0 and world == 1 and not args.profile and not args.no_cpu:
-        result["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_seconds)
+        _, nt, sweep = sweep_reference_threads(args)
+        result["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_seconds, num_threads=nt)
+        result["cpu_baseline"]["threads_swept"] = sweep
     if rank == 0:
         print(json.dumps(result))
     if world > 1:
@@ -486,7 +488,7 @@ def run_e2e(args, torch, local, rank, world):
             "api": "envpool_b200.make(task,'gymnasium').step(numpy actions) -> numpy"}
 
 
-def cpu_baseline(args, budget_s=15.0, steps=None, warmup=3):
+def cpu_baseline(args, budget_s=15.0, steps=None, warmup=3, num_threads=0):
     """The reference's own CPU thread pool (oracle/_ref = its AsyncEnvPool + env headers
     compiled from /root/reference) timed on this box's host cores; falls back to the scalar
     oracle port when _ref is absent."""
@@ -502,16 +504,20 @@ def cpu_baseline(args, budget_s=15.0, steps=None, warmup=3):
             acts = rng.uniform(-2, 2, size=(Ta, n, 1)).astype(np.float32)
         else:
             acts = rng.integers(0, nact, size=(Ta, n)).astype(np.int32)
-        pool = ref_lib.RefPool(eng, n, seed=0, max_episode_steps=ms, iopt=iopt, num_threads=0)
+        pool = ref_lib.RefPool(eng, n, seed=0, max_episode_steps=ms, iopt=iopt,
+                               num_threads=num_threads)
         if steps is None:
             probe = pool.bench(acts, 1, 3) / 3
             steps = int(min(max(budget_s / max(probe, 1e-6), 5), 5000))
         dt = pool.bench(acts, warmup, steps)
         pool.close()
-        return {"value": n * steps / dt, "unit": "env-steps/s", "cores": cores,
+        used = min(n, cores) if num_threads <= 0 else num_threads
+        return {"value": n * steps / dt, "unit": "env-steps/s", "cores": used,
                 "kind": "reference", "ms_per_step": dt / steps * 1e3,
                 "sample": f"{steps} sync steps of the same {n}-env batch workload, "
-                          f"AsyncEnvPool num_threads=min(batch, {cores} hw threads)"}
+                          f"AsyncEnvPool num_threads={used} of {cores} hw threads"
+                          + (" (its default: min(batch, hw threads))" if num_threads <= 0
+                             else "")}
     from oracle.oracle_lib import OraclePool
 
     pool = OraclePool(eng, n, seed=0, max_episode_steps=ms, iopt=iopt)
@@ -536,6 +542,29 @@ def cpu_baseline(args, budget_s=15.0, steps=None, warmup=3):
             "sample": f"{steps} sync steps of the same {n}-env batch, scalar C port"}
 
 
+def sweep_reference_threads(args):
+    """The reference's default thread count (every hardware thread) is not its best on a
+    many-core host: each dequeue is serialised by one semaphore
+    (action_buffer_queue.h:71-80) and the workers spin.  Probe a few thread counts on a
+    moderate batch and give the reference the best one -- its own benchmark script takes
+    num_threads as a knob too (benchmark/test_envpool.py).  Returns (best probe result,
+    best num_threads (0 = the default), {threads: env-steps/s})."""
+    probe_args = argparse.Namespace(**vars(args))
+    probe_args.num_envs = min(args.num_envs, 16384)
+    probe = cpu_baseline(probe_args, steps=3, warmup=1)
+    cores = os.cpu_count() or 1
+    sweep = {str(probe["cores"]): probe["value"]}
+    best = 0
+    if probe["kind"] == "reference":
+        cand = {max(1, cores // d) for d in (2, 4, 8, 16)} | {1, 4}
+        for nt in sorted(cand - {probe["cores"]}):
+            r = cpu_baseline(probe_args, steps=3, warmup=1, num_threads=nt)
+            sweep[str(nt)] = r["value"]
+            if r["value"] > probe["value"]:
+                probe, best = r, nt
+    return probe, best, {k: round(v) for k, v in sweep.items()}
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation of the path (oracle/_ref = its
     AsyncEnvPool + env headers compiled from /root/reference) on this box's host cores, same
@@ -552,13 +581,14 @@ def run_reference(args):
     # probe the per-env-step cost at a moderate batch, then size the per-step sample
     probe_args = argparse.Namespace(**vars(args))
     probe_args.num_envs = min(n_full, 16384)
-    probe = cpu_baseline(probe_args, steps=3, warmup=1)
+    probe, best_threads, sweep = sweep_reference_threads(probe_args)
     rate = max(probe["value"], 1.0)
     n_s = int(min(n_full, max(64, rate * budget_s / max(K + W, 1))))
     if n_s < n_full:
         n_s = 1 << (n_s.bit_length() - 1)   # power of two, >= 64
     args.num_envs = n_s
-    cb = cpu_baseline(args, steps=K, warmup=W)
+    cb = cpu_baseline(args, steps=K, warmup=W, num_threads=best_threads)
+    cb["threads_swept"] = sweep
     if n_s < n_full:
         cb["sample"] = (f"each of the {K} steps is a {n_s}-env batch (bounded sample of the "
                         f"{n_full}-env workload so that the run ends in minutes); "
