@@ -62,10 +62,27 @@ def main():
     import envpool.classic_control.registration  # noqa: F401
     import envpool.toy_text.registration  # noqa: F401
 
+    # mujoco/gym: the reference's family package imports ALL eleven MuJoCo tasks from one
+    # extension module, of which only HalfCheetah exists here.  Stand in for the package
+    # object only (its registration.py and the rest of the layer stay the reference's): the
+    # three HalfCheetah classes are built by the REFERENCE's py_env() over our pybind pair.
+    from envpool.python.api import py_env as ref_py_env
+
+    ours_mj = importlib.import_module("envpool_b200.mujoco.mujoco_gym_envpool")
+    pkg = types.ModuleType("envpool.mujoco.gym")
+    pkg.__path__ = [os.path.join(REF, "envpool", "mujoco", "gym")]
+    (pkg.GymHalfCheetahEnvSpec, pkg.GymHalfCheetahDMEnvPool,
+     pkg.GymHalfCheetahGymnasiumEnvPool) = ref_py_env(ours_mj._GymHalfCheetahEnvSpec,
+                                                      ours_mj._GymHalfCheetahEnvPool)
+    import envpool.mujoco  # noqa: F401  (plain namespace package in the reference)
+
+    sys.modules["envpool.mujoco.gym"] = pkg
+    import envpool.mujoco.gym.registration  # noqa: F401
+
     report["reference_file"] = envpool.__file__
     ref_all = set(envpool.list_all_envs())
     for task, (import_path, spec_cls, _) in sorted(our_registry.specs.items()):
-        if not import_path.endswith(("classic_control", "toy_text")):
+        if not import_path.endswith(("classic_control", "toy_text", "mujoco.gym")):
             continue
         entry = {"in_reference_registry": task in ref_all}
         try:

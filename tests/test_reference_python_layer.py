@@ -42,7 +42,11 @@ def test_reference_layer_was_the_one_imported(report):
 
 def test_reference_make_spec_over_our_modules_equals_ours(report):
     assert not report["errors"], {t: report["tasks"][t].get("error") for t in report["errors"]}
-    assert len(report["tasks"]) >= 20
+    assert len(report["tasks"]) >= 24
+    for v in ("v3", "v4", "v5"):   # via the reference's mujoco/gym registration.py
+        hc = report["tasks"][f"HalfCheetah-{v}"]
+        assert hc["obs_space"]["shape"] == [17] and hc["dm_action"]["shape"] == [6]
+        assert hc["reward_threshold"] == 4800.0
     for task, e in report["tasks"].items():
         assert e["in_reference_registry"], task
         for k in ("config_equal", "state_keys_equal", "action_keys_equal", "obs_space_equal",
