@@ -260,7 +260,10 @@ def run_ours(args):
         if rank == 0:
             result["e2e"] = e2e
     if rank == 0 and world == 1 and not args.profile and not args.no_cpu:
-        _, nt, sweep = sweep_reference_threads(args)
+        try:
+            _, nt, sweep = sweep_reference_threads(args)
+        except Exception as exc:  # the sweep is a courtesy to the baseline, never fatal
+            nt, sweep = 0, {"error": f"{type(exc).__name__}: {exc}"}
         result["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_seconds, num_threads=nt)
         result["cpu_baseline"]["threads_swept"] = sweep
     if rank == 0:
@@ -581,7 +584,11 @@ def run_reference(args):
     # probe the per-env-step cost at a moderate batch, then size the per-step sample
     probe_args = argparse.Namespace(**vars(args))
     probe_args.num_envs = min(n_full, 16384)
-    probe, best_threads, sweep = sweep_reference_threads(probe_args)
+    try:
+        probe, best_threads, sweep = sweep_reference_threads(probe_args)
+    except Exception as exc:  # fall back to the reference's default thread count
+        probe, best_threads = cpu_baseline(probe_args, steps=3, warmup=1), 0
+        sweep = {"error": f"{type(exc).__name__}: {exc}"}
     rate = max(probe["value"], 1.0)
     n_s = int(min(n_full, max(64, rate * budget_s / max(K + W, 1))))
     if n_s < n_full:
