@@ -861,3 +861,22 @@ void epo_mjc_get(const epo_pool* p, int eid, double* s27) {
   memcpy(s27 + 18, mjc_warm_mut(e->mj), sizeof(double) * 9);
 }
 uint32_t epo_debug_draw(epo_pool* p, int eid) { return rng_next(&p->envs[eid].rng); }
+/* RNG recipe hooks for tests/test_oracle_rng_vs_libstdcxx.py: load an engine state
+ * (624 words + read position, the representation std::mt19937's operator<< prints) and
+ * call the restated distributions directly. */
+void epo_debug_set_rng(epo_pool* p, int eid, const uint32_t* mt624, int idx) {
+  epo_rng* r = &p->envs[eid].rng;
+  memcpy(r->mt, mt624, sizeof(r->mt));
+  r->idx = idx;
+  r->norm_has_saved = 0;
+  r->norm_saved = 0.0;
+}
+int epo_debug_uniform_int(epo_pool* p, int eid, int a, int b) {
+  return rng_uniform_int(&p->envs[eid].rng, a, b);
+}
+double epo_debug_uniform_real(epo_pool* p, int eid, double a, double b) {
+  return rng_uniform_real(&p->envs[eid].rng, a, b);
+}
+double epo_debug_normal(epo_pool* p, int eid, double mean, double stddev) {
+  return rng_normal(&p->envs[eid].rng, mean, stddev);
+}

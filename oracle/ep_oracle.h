@@ -67,6 +67,10 @@ void epo_mjc_set(epo_pool* p, int eid, const double* s27, int done, int cur);
 void epo_mjc_get(const epo_pool* p, int eid, double* s27);
 /* raw engine draw from env `eid`'s std::mt19937 (for RNG known-answer tests) */
 uint32_t epo_debug_draw(epo_pool* p, int eid);
+void epo_debug_set_rng(epo_pool* p, int eid, const uint32_t* mt624, int idx);
+int epo_debug_uniform_int(epo_pool* p, int eid, int a, int b);
+double epo_debug_uniform_real(epo_pool* p, int eid, double a, double b);
+double epo_debug_normal(epo_pool* p, int eid, double mean, double stddev);
 
 #ifdef __cplusplus
 }

@@ -91,3 +91,87 @@ def test_window_never_straddles_regenerated_and_old_words_wrongly():
         own = set(range(8 * c, 8 * c + 8))
         assert not (need & own), c
         assert len({w // 8 for w in need if w != (8 * c + 8) % N}) <= 2, c
+
+
+def test_slip_queue_equals_sequential_lemire_including_rejections():
+    """FrozenLake draws one uniform_int(-1, 1) per step.  libstdc++'s Lemire loop
+    (uniform_int_dist.h:252-282, range 3 on a 32-bit engine) rejects exactly the word 0 and
+    redraws; the device kernel (csrc/toytext.cu FrozenLake::pop_slip) turns 8 engine words at
+    a time into 2-bit codes under a marker bit ("3" = rejected word) and pops one code per
+    step.  A rejection has probability 2^-32 per draw, so no sampled GPU test ever reaches it:
+    here both algorithms run on word streams with zeros injected (also at chunk boundaries and
+    back to back) and must produce the same results from the same number of consumed words."""
+    rng = np.random.default_rng(0)
+
+    def sequential(words):
+        out, i = [], 0
+        while True:
+            while i < len(words):
+                w = int(words[i])
+                i += 1
+                p = w * 3
+                lo = p & 0xFFFFFFFF
+                if lo < 3 and lo < ((1 << 32) - 3) % 3:      # t = (2^32 - r) % r = 1
+                    continue                                   # redraw
+                out.append((p >> 32) - 1)
+                break
+            else:
+                return out
+
+    def queued(words):
+        out, i, queue = [], 0, 1                                # marker bit only = empty
+        while True:
+            if queue <= 1:
+                if i + 8 > len(words):
+                    return out
+                chunk = words[i:i + 8]
+                i += 8
+                queue = 1
+                for k in range(7, -1, -1):
+                    w = int(chunk[k])
+                    code = 3 if w == 0 else (w * 3) >> 32
+                    queue = (queue << 2) | code
+                assert queue < (1 << 17)                        # fits beside x|y<<3 in an int32
+            code = queue & 3
+            queue >>= 2
+            if code != 3:
+                out.append(code - 1)
+
+    for trial in range(50):
+        words = rng.integers(0, 2**32, size=8 * 40, dtype=np.uint64)
+        zeros = rng.choice(len(words), size=rng.integers(0, 40), replace=False)
+        words[zeros] = 0
+        if trial % 5 == 0:
+            words[8:19] = 0                                     # a whole chunk and a half
+        a, b = sequential(words), queued(words)
+        assert b == a[:len(b)] and len(a) - len(b) <= 8
+        assert set(a) <= {-1, 0, 1}
+
+
+def test_crafted_table_emits_wanted_words_in_both_representations():
+    """The crafting used by tests/test_gpu_rng_corner_cases.py: words 0..8 zero, words
+    397..404 = untempered wanted outputs -> the next eight draws are the wanted outputs, both
+    for the block twist at position 624 (oracle / std::mt19937) and for the chunk-wise
+    regeneration at mt_idx = 0 (device model), and the two keep agreeing afterwards."""
+    import ctypes
+
+    from oracle import oracle_lib
+    from test_gpu_rng_corner_cases import crafted_table
+
+    L = oracle_lib.lib()
+    L.epo_debug_set_rng.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    rng = np.random.default_rng(9)
+    orc = oracle_lib.OraclePool("CartPole", 1, seed=0, max_episode_steps=500)
+    for _ in range(10):
+        want = [int(x) for x in rng.integers(0, 2**32, size=8)]
+        want[int(rng.integers(0, 8))] = 0
+        want[int(rng.integers(0, 8))] = 0xFFFFFFFF
+        mt = crafted_table(rng, want)
+        L.epo_debug_set_rng(orc.h, 0, mt.ctypes.data, 624)
+        dev = ChunkedMt(0)
+        dev.table = mt.copy().reshape(N // 8, 8)
+        dev.idx = 0
+        got_o = [orc.draw(0) for _ in range(8 + 700)]
+        got_d = [dev.next() for _ in range(8 + 700)]
+        assert got_o[:8] == want and got_d[:8] == want
+        assert got_o == got_d
