@@ -108,6 +108,33 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None}
 
 
+def bind_to_gpu_numa(local: int):
+    """Pin this process (and the pinned host buffers it allocates from now on) to the CPUs of
+    the NUMA node the GPU hangs off: a host thread on the far socket pays the inter-socket
+    hop on every pinned-memory copy and every doorbell.  Returns what was done."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return {"pci": bdf, "node": node, "bound": False}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"pci": bdf, "node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"pci": bdf, "node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as exc:  # never fatal: the bench runs unbound
+        return {"bound": False, "error": f"{type(exc).__name__}: {exc}"}
+
+
 def make_action_stream(torch, task, n, device, min_bytes):
     """[T, N, ...] synthetic actions on the device, larger than L2 so no row is re-read
     while it could still be cached."""
@@ -151,14 +178,23 @@ def run_ours(args):
     K, W = args.steps, args.warmup
     use_graph = not args.no_graph
 
-    def run_steps(count):
-        """`count` sync steps of this rank's shard; actions cycle through the [T, N] stream.
-        Env-id sharding needs no data-path collective: ranks are independent."""
+    def run_steps(count, t0=0):
+        """`count` sync steps of this rank's shard; actions cycle through the [T, N] stream
+        starting at row t0.  Env-id sharding needs no data-path collective."""
+        if count <= T - t0:
+            pool.step_many_device(actions, t0, count, use_graph=use_graph)
+            return
         q, r = divmod(count, T)
         for _ in range(q):
             pool.step_many_device(actions, 0, T, use_graph=use_graph)
         if r:
             pool.step_many_device(actions, 0, r, use_graph=use_graph)
+
+    # A short timed region (the driver passes --steps 20) replays one K-step graph.  It reads
+    # action rows [t_timed, t_timed + K) -- rows the lead-in does not touch and the L2 flush
+    # has evicted -- so the action stream is as cold as in a long run.
+    t_timed = (T // 2) if K <= T // 2 else 0
+    flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
 
     pool.reset_device()
     pool.sync()
@@ -170,27 +206,51 @@ def run_ours(args):
     # load for ~1 s before the timed region starts
     run_steps(W)
     pool.sync()
+    lead_reps = 2
+    if args.profile and use_graph:   # graphs captured outside the timed region
+        run_steps(K)
+        run_steps(K, t_timed)
+        pool.sync()
     if not args.profile:
         t_w = time.time()
         while True:  # also instantiates every CUDA graph the timed region will replay
             run_steps(K)
+            run_steps(K, t_timed)
             pool.sync()
             if time.time() - t_w >= 1.0:
                 break
+        # how many K-step replays keep the GPU busy for ~0.5 ms (the lead-in below)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run_steps(K)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        lead_reps = int(min(200, max(2, 0.5 / max(e0.elapsed_time(e1), 1e-3))))
     launches0 = pool.launch_count
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # Timed region: L2 flush, then an UNTIMED lead-in of the same launches, ev0, the K timed
+    # steps, ev1 -- enqueued back to back with no host synchronisation in between, so the GPU
+    # is still busy with the lead-in while the host enqueues the timed launches and the host's
+    # launch latency stays outside ev0..ev1 whatever --steps is.
+    with torch.cuda.stream(stream):
+        flush.fill_(1)
+    lead_launches = 0
+    if not args.profile:
+        for _ in range(lead_reps):
+            run_steps(K)
+        lead_launches = pool.launch_count - launches0
     ev0.record(stream)
-    run_steps(K)
+    run_steps(K, t_timed)
     ev1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_load1 = time.time()
     ms_total = ev0.elapsed_time(ev1)
-    launches = pool.launch_count - launches0
+    launches = pool.launch_count - launches0 - lead_launches
     if world > 1:
         tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -223,10 +283,14 @@ def run_ours(args):
                        + (", CUDA-graph replay" if use_graph else "")
                        + ("; env ids sharded over ranks, no data-path collective in `value` "
                           "(see with_allgather for the exchange step)" if world > 1 else ""),
-                "l2": f"action stream {actions.numel() * actions.element_size() >> 20} MiB "
-                      f"> 126 MiB L2, each row read once per cycle; the recurrent env state "
-                      f"and output slab ({bpe * n >> 10} KiB) stay on chip by construction "
-                      f"at this num_envs",
+                "l2": f"L2 flushed (256 MiB fill) before the timed region; action stream "
+                      f"{actions.numel() * actions.element_size() >> 20} MiB > 126 MiB L2, "
+                      f"the timed steps read rows the untimed lead-in does not touch; the "
+                      f"recurrent env state and output slab ({bpe * n >> 10} KiB) stay on "
+                      f"chip by construction at this num_envs",
+                "timing": f"CUDA events on the launching stream around exactly {K} steps, "
+                          f"preceded by {lead_reps} untimed replays enqueued without a host "
+                          f"sync (host launch latency outside the window)",
                 "precision": args.precision, "seed": 0,
             },
             "gpu_launches": int(launches),

@@ -36,7 +36,8 @@ ABI_SYMBOLS = [
     "epb_state_layout", "epb_state_export", "epb_state_import", "epb_launch_count",
     "epb_bytes_per_env_step", "epb_exchange_init", "epb_exchange_base", "epb_exchange_attach",
     "epb_exchange_attach_ipc", "epb_step_exchange_device", "epb_exchange_wait",
-    "epb_exchange_status",
+    "epb_exchange_status", "epb_exchange_slice_bytes", "epb_exchange_depth",
+    "epb_step_many_timed", "epb_step_exchange_many_device",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -114,6 +115,12 @@ def load_library() -> ctypes.CDLL:
     L.epb_step_exchange_device.argtypes = [vp, vp, vp]
     L.epb_exchange_wait.argtypes = [vp, vp, pp]
     L.epb_exchange_status.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ci)]
+    L.epb_exchange_slice_bytes.restype = ctypes.c_int64
+    L.epb_exchange_slice_bytes.argtypes = [vp]
+    L.epb_exchange_depth.argtypes = [vp]
+    L.epb_step_many_timed.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, vp,
+                                      ctypes.POINTER(ctypes.c_float)]
+    L.epb_step_exchange_many_device.argtypes = [vp, vp, ci, ci, ci, ci, vp, pp]
     _lib = L
     return L
 
@@ -263,24 +270,63 @@ class CPool:
         return self.recv()
 
     # ---------------------------------------------------------------- device path
+    def _device_arg(self, t, what: str, dtype: np.dtype, rows: Optional[int], row_elems: int):
+        """Device pointer of a caller-supplied buffer.  torch tensors are validated (a policy's
+        argmax is int64, a sampled torque float64: reading those as int32/float32 rows would
+        silently step on garbage) and converted when only dtype / layout differ; a raw integer
+        pointer is taken on trust."""
+        if not hasattr(t, "data_ptr"):
+            return int(t), None, None
+        import torch
+
+        tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.float32): torch.float32,
+               np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
+        if not t.is_cuda:
+            raise ValueError(f"{what} must be a CUDA tensor (use step()/send() for host arrays)")
+        if t.device.index != self.device:
+            raise ValueError(f"{what} lives on cuda:{t.device.index}, the pool on "
+                             f"cuda:{self.device}")
+        if t.dtype != tdt:
+            if t.dtype.is_floating_point != tdt.is_floating_point:
+                raise ValueError(f"{what} has dtype {t.dtype}, the env expects {tdt}")
+            t = t.to(tdt)
+        if not t.is_contiguous():
+            t = t.contiguous()
+        have = t.shape[0] if t.dim() > 0 else 1
+        if rows is not None and (t.numel() != rows * row_elems):
+            raise ValueError(f"{what} has {t.numel()} elements, expected {rows} rows of "
+                             f"{row_elems}")
+        return t.data_ptr(), t, have
+
     def step_device(self, d_action, d_env_ids=None, n: Optional[int] = None, stream=None):
-        """d_action / d_env_ids: torch CUDA tensors (or raw device pointers)."""
-        pa = d_action.data_ptr() if hasattr(d_action, "data_ptr") else int(d_action)
+        """d_action / d_env_ids: torch CUDA tensors (validated; dtype / layout converted when
+        needed) or raw device pointers (trusted).  env ids must lie in [0, num_envs)."""
+        keep = []
         pi = None
         if d_env_ids is not None:
-            pi = d_env_ids.data_ptr() if hasattr(d_env_ids, "data_ptr") else int(d_env_ids)
+            pi, t, have = self._device_arg(d_env_ids, "env_id", np.int32, None, 1)
+            keep.append(t)
+            if n is None and have is not None:
+                n = have
+            if t is not None and n is not None and t.numel() < n:
+                raise ValueError(f"env_id has {t.numel()} elements, n = {n}")
         if n is None:
-            n = d_env_ids.shape[0] if d_env_ids is not None and hasattr(d_env_ids, "shape") \
-                else self.n
+            n = self.n
+        row_elems = self.action_key.row_bytes // self.action_key.dtype.itemsize
+        pa, t, _ = self._device_arg(d_action, "action", self.action_key.dtype, n, row_elems)
+        keep.append(t)
         _check(self.lib.epb_step_device(self.h, pa, pi, n, stream))
+        # converted temporaries must outlive the launch: park them until the next call
+        self._keepalive = keep
 
     def reset_device(self, d_env_ids=None, n: Optional[int] = None, stream=None):
-        pi = None
+        pi, keep = None, None
         if d_env_ids is not None:
-            pi = d_env_ids.data_ptr() if hasattr(d_env_ids, "data_ptr") else int(d_env_ids)
+            pi, keep, have = self._device_arg(d_env_ids, "env_id", np.int32, None, 1)
             if n is None:
-                n = d_env_ids.shape[0]
+                n = have
         _check(self.lib.epb_reset_device(self.h, pi, n if n is not None else self.n, stream))
+        self._keepalive = [keep]
 
     def outputs_device_ptr(self) -> int:
         p = ctypes.c_void_p()
@@ -314,6 +360,16 @@ class CPool:
         _check(self.lib.epb_step_many_device(self.h, d_actions.data_ptr(),
                                              d_actions.shape[0], t0, K,
                                              1 if use_graph else 0, stream))
+
+    def step_many_timed(self, d_actions, t0: int, K: int, mark0: int, mark1: int,
+                        exchange: bool = False, use_graph: bool = True, stream=None) -> float:
+        """The K-step chain with timestamps inside it: milliseconds for steps
+        [mark0, mark1) in the chain's steady state (synchronises the stream)."""
+        ms = ctypes.c_float()
+        _check(self.lib.epb_step_many_timed(self.h, d_actions.data_ptr(), d_actions.shape[0],
+                                            t0, K, mark0, mark1, 1 if exchange else 0,
+                                            1 if use_graph else 0, stream, ctypes.byref(ms)))
+        return float(ms.value)
 
     # ------------------------------------------------------------- peer exchange
     def exchange_init(self, world: int, rank: int) -> bytes:
@@ -352,6 +408,25 @@ class CPool:
         _check(self.lib.epb_exchange_wait(self.h, stream, ctypes.byref(p)))
         return p.value
 
+    def step_exchange_many(self, d_actions, t0: int, K: int, use_graph: bool = True,
+                           stream=None) -> int:
+        """K exchanged steps (waits on a parallel graph branch); returns the device pointer
+        of the last gathered batch, [world][exchange_slice_bytes]."""
+        p = ctypes.c_void_p()
+        _check(self.lib.epb_step_exchange_many_device(self.h, d_actions.data_ptr(),
+                                                      d_actions.shape[0], t0, K,
+                                                      1 if use_graph else 0, stream,
+                                                      ctypes.byref(p)))
+        return p.value
+
+    @property
+    def exchange_slice_bytes(self) -> int:
+        return self.lib.epb_exchange_slice_bytes(self.h)
+
+    @property
+    def exchange_depth(self) -> int:
+        return self.lib.epb_exchange_depth(self.h)
+
     def exchange_status(self):
         steps, bad = ctypes.c_int64(), ctypes.c_int()
         _check(self.lib.epb_exchange_status(self.h, ctypes.byref(steps), ctypes.byref(bad)))
@@ -373,9 +448,10 @@ class CPool:
         return self.lib.epb_bytes_per_env_step(self.h)
 
     def state_layout(self) -> Dict[str, int]:
-        out = (ctypes.c_int64 * 8)()
+        out = (ctypes.c_int64 * 10)()
         _check(self.lib.epb_state_layout(self.h, out))
-        names = ["flags", "mt_idx", "istate", "rstate", "mt", "NI", "NR", "real_size"]
+        names = ["flags", "mt_idx", "istate", "rstate", "mt", "NI", "NR", "real_size",
+                 "rec", "rstat"]
         return dict(zip(names, [int(v) for v in out]))
 
     def state_arrays(self, blob: np.ndarray) -> Dict[str, np.ndarray]:
@@ -393,6 +469,11 @@ class CPool:
             nb = lay["real_size"] * n * lay["NR"]
             out["rstate"] = blob[lay["rstate"]:lay["rstate"] + nb].view(real).reshape(
                 lay["NR"], n)
+        if lay["rec"] >= 0:
+            # reset-ahead records: rec[e] = the env's NEXT initial state, rstat[e] == 1 = full
+            nb = lay["real_size"] * n * lay["NR"]
+            out["rec"] = blob[lay["rec"]:lay["rec"] + nb].view(real).reshape(n, lay["NR"])
+            out["rstat"] = blob[lay["rstat"]:lay["rstat"] + n]
         return out
 
     def state_export(self) -> np.ndarray:

@@ -79,6 +79,17 @@ struct Key {
 
 static int dtype_size(int d) { return d == EPB_F64 ? 8 : d == EPB_BOOL ? 1 : 4; }
 
+// What a cached chain graph was captured for.
+struct ChainKey {
+  const void* actions;
+  int T, t0, K, mark0, mark1, exchange, phase;
+  cudaStream_t stream;
+  bool operator==(const ChainKey& o) const {
+    return actions == o.actions && T == o.T && t0 == o.t0 && K == o.K && mark0 == o.mark0 &&
+           mark1 == o.mark1 && exchange == o.exchange && phase == o.phase && stream == o.stream;
+  }
+};
+
 struct Pending {
   void* slab;
   int n;       // rows written by this send/reset
@@ -123,35 +134,48 @@ struct epb_pool {
   std::mutex mu;
   cudaStream_t stream = nullptr;
   launch_fn step_fn = nullptr, rollout_fn = nullptr;
+  // reset-ahead records (common.cuh StateView::rec): refill launch, step sequence number
+  // (its parity is the consume code) and the side stream + events that put refill(t) on a
+  // parallel branch of the engine's captured step chains
+  launch_fn refill_fn = nullptr;
+  uint64_t seq = 0;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_step[2] = {nullptr, nullptr}, ev_refill[2] = {nullptr, nullptr};
   MjcPool* mjc = nullptr;
   // cached CUDA graphs of K-step chains (epb_step_many_device), most recent first
   struct GraphEntry {
     cudaGraphExec_t exec;
-    const void* actions;
-    int T, t0, K;
-    cudaStream_t stream;
+    ChainKey key;
+    int64_t launches;  // kernels one replay launches
   };
   std::vector<GraphEntry> graphs;
+  int64_t launches_per_chain = 0;
+  // timing marks inside a chain (epb_step_many_timed): timed events + the branch they are
+  // recorded on
+  cudaStream_t mark_side = nullptr;
+  cudaEvent_t ev_mark = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   int64_t launches = 0;
   int bytes_per_step = 0;
-  // peer exchange (exchange.cuh): gather[2][world][slab] | flags[world] | ctl
+  // peer exchange (exchange.cuh):
+  //   slot[D][world][x_slice] | data_flag[16] | ack_flag[16] | ctl | PeerView[D]
   char* x_base = nullptr;
-  int x_world = 0, x_rank = 0;
-  int64_t x_flags_off = 0, x_ctl_off = 0, x_bytes = 0;
+  int x_world = 0, x_rank = 0, x_depth = 4;
+  int64_t x_slice = 0;     // slab_bytes + the packed wire column
+  int64_t x_data_off = 0, x_ack_off = 0, x_ctl_off = 0, x_view_off = 0, x_bytes = 0;
   char* x_peer[kMaxPeers] = {};
   bool x_ipc[kMaxPeers] = {};
   bool x_attached = false;
   long long x_timeout_ns = 10000000000LL;
   bool x_fused = false;  // peer stores issued by the step kernel's epilogue (else push_kernel)
-  uint64_t x_steps = 0;  // host count of exchanged steps; parity picks the gather half
+  uint64_t x_steps = 0;   // host count of exchanged steps; step t uses slot t % D
+  uint64_t x_waited = 0;  // host count of enqueued waits
+  cudaStream_t x_side = nullptr;            // wait branch of the engine-captured chains
+  cudaEvent_t x_ev_step[kMaxDepth] = {}, x_ev_wait[kMaxDepth] = {};
 
-  int64_t x_mine(int parity) const {
-    return ((int64_t)parity * x_world + x_rank) * slab_bytes;
-  }
+  int64_t x_mine(int slot) const { return ((int64_t)slot * x_world + x_rank) * x_slice; }
   ExchangeCtl* x_ctl() const { return reinterpret_cast<ExchangeCtl*>(x_base + x_ctl_off); }
-  // the two per-parity PeerViews live behind the control block, in device memory
-  PeerView* x_view(int parity) const {
-    return reinterpret_cast<PeerView*>(x_base + x_ctl_off + 256) + parity;
+  PeerView* x_view(int slot) const {
+    return reinterpret_cast<PeerView*>(x_base + x_view_off) + slot;
   }
 
   OutView slab_view(char* base) const {
@@ -274,31 +298,39 @@ int get_event(epb_pool* p, cudaEvent_t* ev) {
   return EPB_OK;
 }
 
-// Copy n16 16-byte units of the local slice to every peer, then publish.
+// Copy the wire columns of the local slice to every peer, then publish (families without the
+// forwarding epilogue: HalfCheetah; or ENVPOOL_B200_EXCHANGE=push).  Column k is
+// ceil(n * row_bytes / 16) 16-byte units (the 256-byte column padding absorbs the tail).
 __global__ void __launch_bounds__(256)
-push_kernel(const PeerView* __restrict__ pv, int64_t n16) {
+push_kernel(const PeerView* __restrict__ pv, int n) {
   const int world = pv->world, rank = pv->rank;
-  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(pv->slice[rank]);
+  const char* __restrict__ src = pv->slice[rank];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
-    uint4 v = src[i];
+  for (int k = 0; k < pv->ncols; ++k) {
+    const int64_t off = pv->col_off[k];
+    const int64_t n16 = ((int64_t)n * pv->col_rb[k] + 15) >> 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+      uint4 v = reinterpret_cast<const uint4*>(src + off)[i];
 #pragma unroll 1
-    for (int g = 0; g < world; ++g)
-      if (g != rank) reinterpret_cast<uint4*>(pv->slice[g])[i] = v;
+      for (int g = 0; g < world; ++g)
+        if (g != rank) reinterpret_cast<uint4*>(pv->slice[g] + off)[i] = v;
+    }
   }
   peer_publish(pv);
 }
 
-// One warp: lane g waits until rank g's slice of step `ctl->seq` has landed here.
-// Bounded: `timeout_ns` without progress (default 10 s, ENVPOOL_B200_EXCHANGE_TIMEOUT_S) sets
-// ctl->error instead of hanging the GPU when a peer has died.
-__global__ void wait_kernel(const unsigned long long* flags, int world, ExchangeCtl* ctl,
-                            long long timeout_ns) {
-  const unsigned long long want = ctl->seq;
+// One warp in front of step t (t = ctl->seq, the steps this rank has pushed so far): lane g
+// waits until rank g has released step t - D, i.e. ack_flag[g] >= t - D + 1, so that slot
+// t % D may be overwritten everywhere.  Bounded like the data wait.
+__global__ void credit_kernel(const unsigned long long* ack, int world, int depth,
+                              ExchangeCtl* ctl, long long timeout_ns) {
+  const unsigned long long t = ctl->seq;
+  if (t < (unsigned long long)depth) return;
+  const unsigned long long need = t - depth + 1;
   if ((int)threadIdx.x < world) {
     long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (ld_acquire_sys(flags + threadIdx.x) < want) {
+    while (ld_acquire_sys(ack + threadIdx.x) < need) {
       long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t1 - t0 > timeout_ns) {
@@ -310,38 +342,164 @@ __global__ void wait_kernel(const unsigned long long* flags, int world, Exchange
   }
 }
 
-// Build the two per-parity PeerViews from the attached peer bases and copy them to the device.
+struct WaitArgs {
+  const unsigned long long* data_flag;      // [world] in this rank's allocation
+  unsigned long long* ack_dst[kMaxPeers];   // &ack_flag[rank] in the allocation of rank g
+  char* slots;                              // this rank's slot[0][0]
+  int64_t slice, wire_off;
+  int64_t off_elapsed, off_done, off_discount, off_step_type, off_trunc;
+  ExchangeCtl* ctl;
+  long long timeout_ns;
+  int world, rank, depth, n;
+};
+
+// Wait for step u = ctl->waited of every rank and finish its batch.  Grid (x, world):
+// row g of the grid handles the slice of rank g.  First the release of everything older
+// (ack = u: "steps < u are consumed here" -- the consumer of step u-1 precedes this kernel in
+// stream order), then thread 0 of each CTA acquires data_flag[g] >= u + 1 (bounded: a dead
+// peer sets ctl->error instead of hanging the GPU) and the CTAs of row g re-expand the common
+// columns of rank g's slice from its packed wire column.  Bounded by local HBM, not the link.
+__global__ void __launch_bounds__(256) wait_derive_kernel(WaitArgs a) {
+  ExchangeCtl* ctl = a.ctl;
+  const unsigned long long u = ctl->waited;
+  const int g = blockIdx.y;
+  if (blockIdx.x == 0 && g == 0 && (int)threadIdx.x < a.world)
+    st_release_sys(a.ack_dst[threadIdx.x], u);
+  if (g != a.rank) {
+    if (threadIdx.x == 0) {
+      long long t0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      while (ld_acquire_sys(a.data_flag + g) < u + 1) {
+        long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > a.timeout_ns) {
+          atomicExch(&ctl->error, 1);
+          break;
+        }
+        __nanosleep(32);
+      }
+    }
+    __syncthreads();
+    char* sl = a.slots + ((int64_t)(u % a.depth) * a.world + g) * a.slice;
+    const int4* __restrict__ wire = reinterpret_cast<const int4*>(sl + a.wire_off);
+    int4* elapsed = reinterpret_cast<int4*>(sl + a.off_elapsed);
+    uchar4* done = reinterpret_cast<uchar4*>(sl + a.off_done);
+    float4* discount = reinterpret_cast<float4*>(sl + a.off_discount);
+    int4* step_type = reinterpret_cast<int4*>(sl + a.off_step_type);
+    uchar4* trunc = reinterpret_cast<uchar4*>(sl + a.off_trunc);
+    const int n4 = (a.n + 3) >> 2;  // the tail quad stays inside the 256-byte column padding
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+      const int4 w = __ldcg(wire + i);
+      const int ww[4] = {w.x, w.y, w.z, w.w};
+      int el[4], st[4];
+      unsigned char dn[4], tr[4];
+      float dc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dn[j] = (unsigned char)(ww[j] & 1);
+        tr[j] = (unsigned char)((ww[j] >> 1) & 1);
+        el[j] = ww[j] >> 2;
+        dc[j] = dn[j] ? 0.0f : 1.0f;
+        st[j] = el[j] == 0 ? 0 : (dn[j] ? 2 : 1);
+      }
+      elapsed[i] = make_int4(el[0], el[1], el[2], el[3]);
+      done[i] = make_uchar4(dn[0], dn[1], dn[2], dn[3]);
+      discount[i] = make_float4(dc[0], dc[1], dc[2], dc[3]);
+      step_type[i] = make_int4(st[0], st[1], st[2], st[3]);
+      trunc[i] = make_uchar4(tr[0], tr[1], tr[2], tr[3]);
+    }
+  }
+  // last block done: the next wait kernel handles step u + 1
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    if (atomicAdd(&ctl->wait_blocks, 1u) == total - 1) {
+      ctl->wait_blocks = 0;
+      ctl->waited = u + 1;
+    }
+  }
+}
+
+// info:env_id / info:players.env_id of every rank's slice in every slot never change:
+// rank g owns the global ids [id0 + g * n, id0 + (g + 1) * n).
+__global__ void prefill_ids_kernel(char* slots, int64_t slice, int depth, int world, int n,
+                                   int id0, int64_t off_env_id, int64_t off_players) {
+  const int64_t total = (int64_t)depth * world * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i % n);
+    const int64_t sg = i / n;
+    const int g = (int)(sg % world);
+    char* sl = slots + sg * slice;
+    reinterpret_cast<int32_t*>(sl + off_env_id)[e] = id0 + g * n + e;
+    reinterpret_cast<int32_t*>(sl + off_players)[e] = id0 + g * n + e;
+  }
+}
+
+// Build the per-slot PeerViews from the attached peer bases, copy them to the device and
+// write the constant id columns.
 int upload_views(epb_pool* p) {
-  PeerView v[2];
-  memset(v, 0, sizeof(v));
-  for (int parity = 0; parity < 2; ++parity) {
-    PeerView& pv = v[parity];
+  std::vector<PeerView> v(p->x_depth);
+  memset(v.data(), 0, sizeof(PeerView) * v.size());
+  for (int slot = 0; slot < p->x_depth; ++slot) {
+    PeerView& pv = v[slot];
     pv.world = p->x_world;
     pv.rank = p->x_rank;
     pv.ctl = p->x_ctl();
     for (int g = 0; g < p->x_world; ++g) {
-      pv.slice[g] = p->x_peer[g] + p->x_mine(parity);
+      pv.slice[g] = p->x_peer[g] + p->x_mine(slot);
       pv.flag[g] =
-          reinterpret_cast<unsigned long long*>(p->x_peer[g] + p->x_flags_off) + p->x_rank;
+          reinterpret_cast<unsigned long long*>(p->x_peer[g] + p->x_data_off) + p->x_rank;
     }
-    pv.ncols = (int)p->keys.size();
-    for (int k = 0; k < pv.ncols; ++k) {
-      pv.col_rb[k] = p->keys[k].row_bytes;
-      pv.col_off[k] = p->keys[k].off;
-    }
+    // wire columns: reward, the env keys, the packed common-column word
+    int c = 0;
+    auto add = [&](int rb, int64_t off) {
+      pv.col_rb[c] = rb;
+      pv.col_off[c] = off;
+      ++c;
+    };
+    add(p->keys[4].row_bytes, p->keys[4].off);
+    for (size_t k = 8; k < p->keys.size(); ++k) add(p->keys[k].row_bytes, p->keys[k].off);
+    add(4, p->slab_bytes);
+    pv.ncols = c;
   }
-  EPB_CUDA(cudaMemcpy(p->x_view(0), v, sizeof(v), cudaMemcpyHostToDevice));
+  EPB_CUDA(cudaMemcpy(p->x_view(0), v.data(), sizeof(PeerView) * v.size(),
+                      cudaMemcpyHostToDevice));
+  prefill_ids_kernel<<<148 * 4, 256, 0, p->stream>>>(
+      p->x_base, p->x_slice, p->x_depth, p->x_world, p->N,
+      p->cfg.env_id_offset - p->x_rank * p->N, p->keys[0].off, p->keys[1].off);
+  EPB_CUDA(cudaGetLastError());
+  ++p->launches;
+  EPB_CUDA(cudaStreamSynchronize(p->stream));
   p->x_attached = true;
   return EPB_OK;
 }
 
+// Refill every record consumed with `code` (0 = all that are not full) on `stream`.
+int launch_refill(epb_pool* p, int code, cudaStream_t stream) {
+  LaunchArgs a{};
+  a.sv = p->sv;
+  a.stream = stream;
+  a.refill_code = code;
+  EPB_CUDA(p->refill_fn(a));
+  ++p->launches;
+  return EPB_OK;
+}
+
 // Launch one batch step on `stream`.  d_action/d_ids are device pointers.
+// Record envs: the step is followed by the refill of the records it consumed -- on the same
+// stream (chain_k < 0: direct launches and user-driven captures), or, for step k of an
+// engine-captured chain (chain_k >= 0), on the pool's side stream so that refill(k) runs
+// beside step k+1; step k+2 waits for it (the caller enqueues that wait and the final join).
 int launch_batch(epb_pool* p, const void* d_action, const int32_t* d_ids, int n,
                  int force_reset, char* d_slab, cudaStream_t stream,
-                 const PeerView* peers = nullptr) {
+                 const PeerView* peers = nullptr, int chain_k = -1, int32_t* wire = nullptr,
+                 const void* next_action = nullptr) {
   p->d_last = d_slab;
   if (p->kind == EPB_HALF_CHEETAH) {
-    EPB_CUDA(mjc_launch_step(p->mjc, p->sv, p->slab_view(d_slab),
+    OutView hov = p->slab_view(d_slab);
+    hov.wire = wire;
+    EPB_CUDA(mjc_launch_step(p->mjc, p->sv, hov,
                              static_cast<const double*>(d_action), d_ids, n, force_reset,
                              stream));
     ++p->launches;
@@ -349,15 +507,29 @@ int launch_batch(epb_pool* p, const void* d_action, const int32_t* d_ids, int n,
   }
   LaunchArgs a{};
   a.sv = p->sv;
+  const int code = 2 + (int)(p->seq & 1);
+  a.sv.rec_code = code;
   a.ov = p->slab_view(d_slab);
+  a.ov.wire = wire;
   a.action = d_action;
   a.env_ids = d_ids;
   a.n = n;
   a.force_reset = force_reset;
   a.stream = stream;
   a.peers = peers;
+  a.next_action = next_action;
   EPB_CUDA(p->step_fn(a));
   ++p->launches;
+  ++p->seq;
+  if (p->refill_fn) {
+    if (chain_k < 0) return launch_refill(p, code, stream);
+    const int h = chain_k & 1;
+    EPB_CUDA(cudaEventRecord(p->ev_step[h], stream));
+    EPB_CUDA(cudaStreamWaitEvent(p->side, p->ev_step[h], 0));
+    int rc = launch_refill(p, code, p->side);
+    if (rc != EPB_OK) return rc;
+    EPB_CUDA(cudaEventRecord(p->ev_refill[h], p->side));
+  }
   return EPB_OK;
 }
 
@@ -494,7 +666,10 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
   int64_t o_ist = o_idx + al(4 * N);
   int64_t o_rst = o_ist + al(4 * N * (p->NI > 0 ? p->NI : 1));
   int64_t o_mt = o_rst + al((int64_t)p->real_size * N * (p->NR > 0 ? p->NR : 1));
-  p->state_bytes = o_mt + al(4 * N * kMtN);
+  const bool has_rec = kind <= EPB_MOUNTAIN_CAR_CONTINUOUS;  // classic_control: record resets
+  int64_t o_rec = o_mt + al(4 * N * kMtN);
+  int64_t o_rstat = o_rec + (has_rec ? al((int64_t)p->real_size * N * p->NR) : 0);
+  p->state_bytes = o_rstat + (has_rec ? al(N) : 0);
   cudaError_t e = cudaMalloc(&p->d_state_blob, (size_t)p->state_bytes);
   if (e == cudaSuccess) e = cudaMemset(p->d_state_blob, 0, (size_t)p->state_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&p->d_slab, (size_t)p->slab_bytes);
@@ -509,6 +684,20 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->h_stage_ev[f], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaStreamCreate(&p->stream);  // blocking: ordered with the legacy default stream (torch interop)
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->mark_side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->x_side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_mark, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreate(&p->ev_t0);
+  if (e == cudaSuccess) e = cudaEventCreate(&p->ev_t1);
+  for (int h = 0; h < kMaxDepth && e == cudaSuccess; ++h) {
+    e = cudaEventCreateWithFlags(&p->x_ev_step[h], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->x_ev_wait[h], cudaEventDisableTiming);
+  }
+  for (int h = 0; h < 2 && e == cudaSuccess; ++h) {
+    e = cudaEventCreateWithFlags(&p->ev_step[h], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_refill[h], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
     std::string msg = std::string("device allocation: ") + cudaGetErrorString(e);
     epb_destroy(p);
@@ -527,10 +716,20 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
   p->sv.istate = reinterpret_cast<int32_t*>(blob + o_ist);
   p->sv.rstate = blob + o_rst;
   p->sv.mt = reinterpret_cast<uint32_t*>(blob + o_mt);
+  if (has_rec) {
+    p->sv.rec = blob + o_rec;
+    p->sv.rstat = reinterpret_cast<uint8_t*>(blob + o_rstat);
+    // Load the record with the state while state + records + slab stay L2-resident; for
+    // larger batches only the resetting lanes fetch it.  ENVPOOL_B200_REC_SPEC=0|1 overrides.
+    p->sv.rec_spec = N <= 262144 ? 1 : 0;
+    if (const char* rs = getenv("ENVPOOL_B200_REC_SPEC")) p->sv.rec_spec = rs[0] == '1';
+    p->sv.rec_code = 2;
+  }
 
   if (kind <= EPB_MOUNTAIN_CAR_CONTINUOUS) {
     p->step_fn = classic_step_fn(kind, p->precision);
     p->rollout_fn = classic_rollout_fn(kind, p->precision);
+    p->refill_fn = classic_refill_fn(kind, p->precision);
   } else if (kind <= EPB_BLACKJACK) {
     p->step_fn = toytext_step_fn(kind, iopt);
     p->rollout_fn = toytext_rollout_fn(kind, iopt);
@@ -546,6 +745,14 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
   if (e == cudaSuccess) {
     seed_kernel<<<(p->N + 127) / 128, 128, 0, p->stream>>>(p->sv, cfg->seed, d_env_seed);
     e = cudaGetLastError();
+    ++p->launches;
+  }
+  if (e == cudaSuccess && p->refill_fn) {  // first records (rstat was zeroed: none is full)
+    LaunchArgs ra{};
+    ra.sv = p->sv;
+    ra.stream = p->stream;
+    ra.refill_code = 0;
+    e = p->refill_fn(ra);
     ++p->launches;
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
@@ -589,6 +796,22 @@ int epb_destroy(epb_pool* p) {
   if (p->d_slab) cudaFree(p->d_slab);
   if (p->d_action) cudaFree(p->d_action);
   if (p->d_ids) cudaFree(p->d_ids);
+  for (cudaStream_t* st : {&p->side, &p->mark_side, &p->x_side}) {
+    if (*st) {
+      cudaStreamSynchronize(*st);
+      cudaStreamDestroy(*st);
+    }
+  }
+  for (cudaEvent_t ev : {p->ev_mark, p->ev_t0, p->ev_t1})
+    if (ev) cudaEventDestroy(ev);
+  for (int h = 0; h < kMaxDepth; ++h) {
+    if (p->x_ev_step[h]) cudaEventDestroy(p->x_ev_step[h]);
+    if (p->x_ev_wait[h]) cudaEventDestroy(p->x_ev_wait[h]);
+  }
+  for (int h = 0; h < 2; ++h) {
+    if (p->ev_step[h]) cudaEventDestroy(p->ev_step[h]);
+    if (p->ev_refill[h]) cudaEventDestroy(p->ev_refill[h]);
+  }
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
   return EPB_OK;
@@ -806,51 +1029,187 @@ int epb_rollout_device(epb_pool* p, const void* d_actions, int T, void* const* d
   return EPB_OK;
 }
 
-int epb_step_many_device(epb_pool* p, const void* d_actions, int T_stream, int t0, int K,
-                         int use_graph, void* stream) {
+namespace {
+
+int exchange_step(epb_pool* p, const void* d_action, cudaStream_t s, int chain_k,
+                  const void* next_action);
+int exchange_wait_launch(epb_pool* p, cudaStream_t s);
+
+// K consecutive sync steps on `st`, step k reading action row (t0 + k) % T.  `fork` (only
+// while capturing) puts the off-critical-path kernels on parallel graph branches:
+//   * refill(k) (record envs) on p->side: beside step k+1, awaited by step k+2;
+//   * exchange chains: wait_derive(k) on p->x_side: step k+1 .. k+D-2 compute and push while
+//     the batch of step k is still arriving; step k+D-1 waits for it (its credit needs the
+//     local release as well as the peers');
+//   * timing marks: ev0 takes the timestamp at which step mark0 became ready, ev1 the
+//     completion of step mark1-1 -- recorded on a branch of their own, not in series.
+int run_chain(epb_pool* p, cudaStream_t st, const ChainKey& c, bool fork, cudaEvent_t ev0,
+              cudaEvent_t ev1) {
+  const size_t row = (size_t)p->act.row_bytes * p->N;
+  const char* base = static_cast<const char*>(c.actions);
+  const bool rec = fork && p->refill_fn;
+  const bool xfork = fork && c.exchange;
+  const int D = p->x_depth;
+  auto mark = [&](cudaEvent_t ev) -> int {
+    if (!fork) {
+      EPB_CUDA(cudaEventRecord(ev, st));
+      return EPB_OK;
+    }
+    EPB_CUDA(cudaEventRecord(p->ev_mark, st));
+    EPB_CUDA(cudaStreamWaitEvent(p->mark_side, p->ev_mark, 0));
+    EPB_CUDA(cudaEventRecordWithFlags(ev, p->mark_side, cudaEventRecordExternal));
+    return EPB_OK;
+  };
+  bool marked = false;
+  for (int k = 0; k < c.K; ++k) {
+    const char* a = base + row * ((c.t0 + k) % c.T);
+    const char* nx = base + row * ((c.t0 + k + 1) % c.T);
+    if (ev0 && k == c.mark0) {
+      int rc = mark(ev0);
+      if (rc != EPB_OK) return rc;
+      marked = true;
+    }
+    if (rec && k >= 2) EPB_CUDA(cudaStreamWaitEvent(st, p->ev_refill[k & 1], 0));
+    int rc;
+    if (c.exchange) {
+      if (xfork && k >= D - 1)
+        EPB_CUDA(cudaStreamWaitEvent(st, p->x_ev_wait[(k - (D - 1)) % D], 0));
+      rc = exchange_step(p, a, st, rec ? k : -1, nx);
+      if (rc != EPB_OK) return rc;
+      if (xfork) {
+        EPB_CUDA(cudaEventRecord(p->x_ev_step[k % D], st));
+        EPB_CUDA(cudaStreamWaitEvent(p->x_side, p->x_ev_step[k % D], 0));
+        rc = exchange_wait_launch(p, p->x_side);
+        if (rc != EPB_OK) return rc;
+        EPB_CUDA(cudaEventRecord(p->x_ev_wait[k % D], p->x_side));
+      } else {
+        rc = exchange_wait_launch(p, st);
+        if (rc != EPB_OK) return rc;
+      }
+    } else {
+      rc = launch_batch(p, a, nullptr, p->N, 0, p->d_slab, st, nullptr, rec ? k : -1, nullptr,
+                        nx);
+      if (rc != EPB_OK) return rc;
+    }
+    if (ev1 && k + 1 == c.mark1) {
+      if (xfork) {  // an exchanged step is complete when its batch has arrived
+        EPB_CUDA(cudaStreamWaitEvent(p->mark_side, p->x_ev_wait[k % D], 0));
+        EPB_CUDA(cudaEventRecordWithFlags(ev1, p->mark_side, cudaEventRecordExternal));
+      } else {
+        rc = mark(ev1);
+        if (rc != EPB_OK) return rc;
+      }
+    }
+  }
+  // join every branch
+  if (rec) {
+    EPB_CUDA(cudaStreamWaitEvent(st, p->ev_refill[(c.K - 1) & 1], 0));
+    if (c.K >= 2) EPB_CUDA(cudaStreamWaitEvent(st, p->ev_refill[(c.K - 2) & 1], 0));
+  }
+  if (xfork) EPB_CUDA(cudaStreamWaitEvent(st, p->x_ev_wait[(c.K - 1) % D], 0));
+  if (fork && (marked || (ev1 && c.mark1 > 0))) {
+    EPB_CUDA(cudaEventRecord(p->ev_mark, p->mark_side));
+    EPB_CUDA(cudaStreamWaitEvent(st, p->ev_mark, 0));
+  }
+  return EPB_OK;
+}
+
+int chain_entry(epb_pool* p, const void* d_actions, int T_stream, int t0, int K, int use_graph,
+                void* stream, int exchange, int mark0, int mark1, float* ms_out) {
   if (!p || !d_actions) return fail(EPB_ERR_INVALID, "null argument");
   if (T_stream <= 0 || K <= 0 || t0 < 0) return fail(EPB_ERR_INVALID, "bad step-chain shape");
+  const bool timed = ms_out != nullptr;
+  if (timed && !(0 <= mark0 && mark0 < mark1 && mark1 <= K))
+    return fail(EPB_ERR_INVALID, "timing marks must satisfy 0 <= mark0 < mark1 <= K");
+  if (exchange) {
+    if (!p->x_attached) return fail(EPB_ERR_STATE, "exchange: peers not attached");
+    if (p->x_waited != p->x_steps)
+      return fail(EPB_ERR_STATE, "exchange chain: an exchanged step has not been waited for");
+  }
   DeviceGuard guard(p->cfg.device);
   EPB_CUDA(guard.status);
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
-  const size_t row = (size_t)p->act.row_bytes * p->N;
-  auto chain = [&](cudaStream_t st) -> int {
-    for (int k = 0; k < K; ++k) {
-      const char* a = static_cast<const char*>(d_actions) + row * ((t0 + k) % T_stream);
-      int rc = launch_batch(p, a, nullptr, p->N, 0, p->d_slab, st);
-      if (rc != EPB_OK) return rc;
+  ChainKey key{d_actions, T_stream, t0, K, timed ? mark0 : -1, timed ? mark1 : -1, exchange,
+               exchange ? (int)(p->x_steps % p->x_depth) : 0, s};
+  cudaEvent_t ev0 = timed ? p->ev_t0 : nullptr, ev1 = timed ? p->ev_t1 : nullptr;
+  if (!use_graph) {
+    int rc = run_chain(p, s, key, false, ev0, ev1);
+    if (rc != EPB_OK) return rc;
+  } else {
+    cudaGraphExec_t exec = nullptr;
+    for (const auto& g : p->graphs)
+      if (g.key == key) exec = g.exec;
+    if (!exec) {
+      if (p->graphs.size() >= 8) {
+        cudaGraphExecDestroy(p->graphs.back().exec);
+        p->graphs.pop_back();
+      }
+      cudaGraph_t g = nullptr;
+      EPB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const int64_t before = p->launches;
+      const uint64_t xs = p->x_steps, xw = p->x_waited, sq = p->seq;
+      static const bool no_fork = [] {
+        const char* e = getenv("ENVPOOL_B200_REFILL_FORK");
+        return e && e[0] == '0';
+      }();
+      int rc = run_chain(p, s, key, !no_fork, ev0, ev1);
+      p->launches_per_chain = p->launches - before;
+      p->launches = before;  // capture records, it does not launch
+      p->x_steps = xs;
+      p->x_waited = xw;
+      p->seq = sq;
+      cudaError_t e = cudaStreamEndCapture(s, &g);
+      if (rc != EPB_OK) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+      }
+      if (e != cudaSuccess)
+        return fail(EPB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&exec, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess)
+        return fail(EPB_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+      p->graphs.insert(p->graphs.begin(),
+                       epb_pool::GraphEntry{exec, key, p->launches_per_chain});
     }
-    return EPB_OK;
-  };
-  if (!use_graph) return chain(s);
-  cudaGraphExec_t exec = nullptr;
-  for (const auto& g : p->graphs)
-    if (g.actions == d_actions && g.T == T_stream && g.t0 == t0 && g.K == K && g.stream == s)
-      exec = g.exec;
-  if (!exec) {
-    if (p->graphs.size() >= 4) {
-      cudaGraphExecDestroy(p->graphs.back().exec);
-      p->graphs.pop_back();
+    int64_t per = 0;
+    for (const auto& g : p->graphs)
+      if (g.exec == exec) per = g.launches;
+    EPB_CUDA(cudaGraphLaunch(exec, s));
+    p->launches += per;
+    p->seq += (uint64_t)K;
+    if (exchange) {
+      p->x_steps += (uint64_t)K;
+      p->x_waited += (uint64_t)K;
     }
-    cudaGraph_t g = nullptr;
-    EPB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    const int64_t before = p->launches;
-    int rc = chain(s);
-    p->launches = before;  // capture records, it does not launch
-    cudaError_t e = cudaStreamEndCapture(s, &g);
-    if (rc != EPB_OK) {
-      if (g) cudaGraphDestroy(g);
-      return rc;
-    }
-    if (e != cudaSuccess) return fail(EPB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&exec, g, 0);
-    cudaGraphDestroy(g);
-    if (e != cudaSuccess) return fail(EPB_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
-    p->graphs.insert(p->graphs.begin(), epb_pool::GraphEntry{exec, d_actions, T_stream, t0, K, s});
   }
-  EPB_CUDA(cudaGraphLaunch(exec, s));
-  p->launches += K;
+  if (exchange) p->d_last = p->x_base + p->x_mine((int)((p->x_steps - 1) % p->x_depth));
+  if (timed) {
+    EPB_CUDA(cudaStreamSynchronize(s));
+    EPB_CUDA(cudaEventElapsedTime(ms_out, p->ev_t0, p->ev_t1));
+  }
   return EPB_OK;
+}
+
+}  // namespace
+
+int epb_step_many_device(epb_pool* p, const void* d_actions, int T_stream, int t0, int K,
+                         int use_graph, void* stream) {
+  return chain_entry(p, d_actions, T_stream, t0, K, use_graph, stream, 0, 0, 0, nullptr);
+}
+int epb_step_many_timed(epb_pool* p, const void* d_actions, int T_stream, int t0, int K,
+                        int mark0, int mark1, int exchange, int use_graph, void* stream,
+                        float* ms_out) {
+  if (!ms_out) return fail(EPB_ERR_INVALID, "null argument");
+  return chain_entry(p, d_actions, T_stream, t0, K, use_graph, stream, exchange, mark0, mark1,
+                     ms_out);
+}
+int epb_step_exchange_many_device(epb_pool* p, const void* d_actions, int T_stream, int t0,
+                                  int K, int use_graph, void* stream, void** d_gathered) {
+  int rc = chain_entry(p, d_actions, T_stream, t0, K, use_graph, stream, 1, 0, 0, nullptr);
+  if (rc == EPB_OK && d_gathered)
+    *d_gathered = p->x_base + (int64_t)((p->x_steps - 1) % p->x_depth) * p->x_world * p->x_slice;
+  return rc;
 }
 
 // ---- peer exchange ---------------------------------------------------------------------
@@ -862,9 +1221,16 @@ int epb_exchange_init(epb_pool* p, int world, int rank, void* ipc_handle_out) {
   static_assert(sizeof(cudaIpcMemHandle_t) == EPB_IPC_HANDLE_BYTES, "IPC handle size");
   DeviceGuard guard(p->cfg.device);
   EPB_CUDA(guard.status);
-  p->x_flags_off = 2 * (int64_t)world * p->slab_bytes;
-  p->x_ctl_off = p->x_flags_off + 256;
-  p->x_bytes = p->x_ctl_off + 256 + ((2 * (int64_t)sizeof(PeerView) + 255) / 256) * 256;
+  if (const char* d = getenv("ENVPOOL_B200_EXCHANGE_DEPTH")) {
+    int v = atoi(d);
+    if (v >= 2 && v <= kMaxDepth) p->x_depth = v;
+  }
+  p->x_slice = p->slab_bytes + (((int64_t)4 * p->N + 255) / 256) * 256;
+  p->x_data_off = (int64_t)p->x_depth * world * p->x_slice;
+  p->x_ack_off = p->x_data_off + 8 * kMaxPeers;
+  p->x_ctl_off = p->x_ack_off + 8 * kMaxPeers;
+  p->x_view_off = p->x_ctl_off + 256;
+  p->x_bytes = p->x_view_off + (((int64_t)p->x_depth * sizeof(PeerView) + 255) / 256) * 256;
   EPB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->x_base), (size_t)p->x_bytes));
   EPB_CUDA(cudaMemset(p->x_base, 0, (size_t)p->x_bytes));
   EPB_CUDA(cudaDeviceSynchronize());
@@ -896,6 +1262,8 @@ int epb_exchange_base(const epb_pool* p, void** base, int64_t* bytes) {
   if (bytes) *bytes = p->x_bytes;
   return EPB_OK;
 }
+int64_t epb_exchange_slice_bytes(const epb_pool* p) { return p ? p->x_slice : 0; }
+int epb_exchange_depth(const epb_pool* p) { return p ? p->x_depth : 0; }
 int epb_exchange_attach(epb_pool* p, void* const* peer_bases) {
   if (!p || !peer_bases) return fail(EPB_ERR_INVALID, "null argument");
   if (!p->x_base) return fail(EPB_ERR_STATE, "exchange not initialised");
@@ -924,46 +1292,106 @@ int epb_exchange_attach_ipc(epb_pool* p, const void* ipc_handles) {
   }
   return upload_views(p);
 }
-int epb_step_exchange_device(epb_pool* p, const void* d_action, void* stream) {
-  if (!p) return fail(EPB_ERR_INVALID, "null pool");
-  if (!p->x_attached) return fail(EPB_ERR_STATE, "exchange: peers not attached");
-  DeviceGuard guard(p->cfg.device);
-  EPB_CUDA(guard.status);
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
-  const int parity = (int)(p->x_steps & 1);
-  char* mine = p->x_base + p->x_mine(parity);
+
+namespace {
+
+// One exchanged step on `s`: credit (slot t % D is free everywhere), the step kernel writing
+// slot[t % D][rank] of the local allocation and forwarding its wire columns, publication.
+int exchange_step(epb_pool* p, const void* d_action, cudaStream_t s, int chain_k,
+                  const void* next_action) {
+  const int D = p->x_depth;
+  const uint64_t t = p->x_steps;
+  // the credit of step t needs this rank's own release of step t - D, which its wait for
+  // step t - D + 1 publishes: that wait must at least have been enqueued
+  if (t + 2 > p->x_waited + (uint64_t)D)
+    return fail(EPB_ERR_STATE,
+                "exchange: too many exchanged steps without epb_exchange_wait (at most "
+                "depth - 1 may be outstanding)");
+  const int slot = (int)(t % D);
+  if (t >= (uint64_t)D || p->x_world > 0) {
+    credit_kernel<<<1, 32, 0, s>>>(
+        reinterpret_cast<const unsigned long long*>(p->x_base + p->x_ack_off), p->x_world, D,
+        p->x_ctl(), p->x_timeout_ns);
+    EPB_CUDA(cudaGetLastError());
+    ++p->launches;
+  }
+  char* mine = p->x_base + p->x_mine(slot);
+  int32_t* wire = reinterpret_cast<int32_t*>(mine + p->slab_bytes);
   const int force = d_action ? 0 : 1;
   if (p->x_fused) {
-    int rc = launch_batch(p, d_action, nullptr, p->N, force, mine, s, p->x_view(parity));
+    int rc = launch_batch(p, d_action, nullptr, p->N, force, mine, s, p->x_view(slot), chain_k,
+                          wire, next_action);
     if (rc != EPB_OK) return rc;
   } else {
-    int rc = launch_batch(p, d_action, nullptr, p->N, force, mine, s);
+    int rc = launch_batch(p, d_action, nullptr, p->N, force, mine, s, nullptr, chain_k, wire,
+                          next_action);
     if (rc != EPB_OK) return rc;
-    const int64_t n16 = p->slab_bytes / 16;
+    int64_t n16 = 0;
+    for (size_t k = 8; k < p->keys.size(); ++k)
+      n16 += ((int64_t)p->N * p->keys[k].row_bytes + 15) / 16;
     int64_t blocks = (n16 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    push_kernel<<<(unsigned)blocks, 256, 0, s>>>(p->x_view(parity), n16);
+    push_kernel<<<(unsigned)blocks, 256, 0, s>>>(p->x_view(slot), p->N);
     EPB_CUDA(cudaGetLastError());
     ++p->launches;
   }
   ++p->x_steps;
   return EPB_OK;
 }
-int epb_exchange_wait(epb_pool* p, void* stream, void** d_gathered) {
+
+// The wait for the oldest exchanged step that has not been waited for (step u = x_waited).
+int exchange_wait_launch(epb_pool* p, cudaStream_t s) {
+  WaitArgs a{};
+  a.data_flag = reinterpret_cast<const unsigned long long*>(p->x_base + p->x_data_off);
+  for (int g = 0; g < p->x_world; ++g)
+    a.ack_dst[g] =
+        reinterpret_cast<unsigned long long*>(p->x_peer[g] + p->x_ack_off) + p->x_rank;
+  a.slots = p->x_base;
+  a.slice = p->x_slice;
+  a.wire_off = p->slab_bytes;
+  a.off_elapsed = p->keys[2].off;
+  a.off_done = p->keys[3].off;
+  a.off_discount = p->keys[5].off;
+  a.off_step_type = p->keys[6].off;
+  a.off_trunc = p->keys[7].off;
+  a.ctl = p->x_ctl();
+  a.timeout_ns = p->x_timeout_ns;
+  a.world = p->x_world;
+  a.rank = p->x_rank;
+  a.depth = p->x_depth;
+  a.n = p->N;
+  int per_peer = (p->N / 4 + 255) / 256;
+  if (per_peer > 16) per_peer = 16;
+  if (per_peer < 1) per_peer = 1;
+  wait_derive_kernel<<<dim3(per_peer, p->x_world), 256, 0, s>>>(a);
+  EPB_CUDA(cudaGetLastError());
+  ++p->launches;
+  ++p->x_waited;
+  return EPB_OK;
+}
+
+}  // namespace
+
+int epb_step_exchange_device(epb_pool* p, const void* d_action, void* stream) {
   if (!p) return fail(EPB_ERR_INVALID, "null pool");
-  if (!p->x_attached || p->x_steps == 0)
-    return fail(EPB_ERR_STATE, "exchange: nothing has been exchanged yet");
+  if (!p->x_attached) return fail(EPB_ERR_STATE, "exchange: peers not attached");
   DeviceGuard guard(p->cfg.device);
   EPB_CUDA(guard.status);
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
-  wait_kernel<<<1, 32, 0, s>>>(
-      reinterpret_cast<const unsigned long long*>(p->x_base + p->x_flags_off), p->x_world,
-      p->x_ctl(), p->x_timeout_ns);
-  EPB_CUDA(cudaGetLastError());
-  ++p->launches;
-  if (d_gathered)
-    *d_gathered = p->x_base + (int64_t)((p->x_steps - 1) & 1) * p->x_world * p->slab_bytes;
+  return exchange_step(p, d_action, s, -1, nullptr);
+}
+int epb_exchange_wait(epb_pool* p, void* stream, void** d_gathered) {
+  if (!p) return fail(EPB_ERR_INVALID, "null pool");
+  if (!p->x_attached || p->x_waited >= p->x_steps)
+    return fail(EPB_ERR_STATE, "exchange: no exchanged step is waiting to be received");
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
+  const int slot = (int)(p->x_waited % p->x_depth);
+  int rc = exchange_wait_launch(p, s);
+  if (rc != EPB_OK) return rc;
+  if (d_gathered) *d_gathered = p->x_base + (int64_t)slot * p->x_world * p->x_slice;
   return EPB_OK;
 }
 int epb_exchange_status(epb_pool* p, int64_t* steps_pushed, int* timed_out) {
@@ -999,6 +1427,8 @@ int epb_state_layout(const epb_pool* p, int64_t* out) {
   out[5] = p->NI;
   out[6] = p->NR;
   out[7] = p->real_size;
+  out[8] = p->sv.rec ? static_cast<const char*>(p->sv.rec) - blob : -1;
+  out[9] = p->sv.rstat ? reinterpret_cast<const char*>(p->sv.rstat) - blob : -1;
   return EPB_OK;
 }
 int epb_state_export(epb_pool* p, void* host_dst) {
@@ -1015,6 +1445,13 @@ int epb_state_import(epb_pool* p, const void* host_src) {
   EPB_CUDA(guard.status);
   EPB_CUDA(cudaStreamSynchronize(p->stream));
   EPB_CUDA(cudaMemcpy(p->d_state_blob, host_src, (size_t)p->state_bytes, cudaMemcpyHostToDevice));
+  if (p->refill_fn) {
+    // a blob may carry records marked not-full (a hand-edited RNG table wants its next reset
+    // drawn from that table): draw them now, so every record is full before the next step
+    int rc = launch_refill(p, 0, p->stream);
+    if (rc != EPB_OK) return rc;
+    EPB_CUDA(cudaStreamSynchronize(p->stream));
+  }
   return EPB_OK;
 }
 

@@ -15,18 +15,59 @@ namespace epb {
 #define M_PI 3.14159265358979323846
 #endif
 
+__device__ __forceinline__ void sincos_small(double x, double* s, double* c);
+
 template <typename R> struct M;
 template <> struct M<double> {
+  static __device__ __forceinline__ void sincos_small_(double x, double* s, double* c) {
+    sincos_small(x, s, c);
+  }
   static __device__ __forceinline__ double sin_(double x) { return sin(x); }
   static __device__ __forceinline__ double cos_(double x) { return cos(x); }
   // one argument reduction for both; same values as sin(x), cos(x)
   static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
 };
 template <> struct M<float> {
+  static __device__ __forceinline__ void sincos_small_(float x, float* s, float* c) {
+    sincosf(x, s, c);
+  }
   static __device__ __forceinline__ float sin_(float x) { return sinf(x); }
   static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
   static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
 };
+
+// sin and cos of a SMALL angle (|x| <= 0.5 rad; CartPole's pole is inside +-0.21 while the
+// episode lives): Taylor polynomials in x^2 to x^17 / x^16 (truncation < 2e-22, i.e. below
+// half an ulp), two independent Horner chains of explicit FMAs -- no argument reduction, no
+// quadrant selection, ~1/3 of the dependent latency of the generic routine.  Results are
+// within 1 ulp, like CUDA's sincos (the reference's glibc is correctly rounded in almost all
+// cases; the parity tests hold both to 1e-6).  Larger angles take the generic path.
+__device__ __forceinline__ void sincos_small(double x, double* s, double* c) {
+  if (fabs(x) > 0.5) {
+    sincos(x, s, c);
+    return;
+  }
+  const double z = __dmul_rn(x, x);
+  double ps = -1.0 / 355687428096000.0;           // -1/17!
+  ps = __fma_rn(ps, z, 1.0 / 1307674368000.0);    //  1/15!
+  ps = __fma_rn(ps, z, -1.0 / 6227020800.0);      // -1/13!
+  ps = __fma_rn(ps, z, 1.0 / 39916800.0);         //  1/11!
+  ps = __fma_rn(ps, z, -1.0 / 362880.0);          // -1/9!
+  ps = __fma_rn(ps, z, 1.0 / 5040.0);             //  1/7!
+  ps = __fma_rn(ps, z, -1.0 / 120.0);             // -1/5!
+  ps = __fma_rn(ps, z, 1.0 / 6.0);                //  1/3!  (sign folded below)
+  double pc = 1.0 / 20922789888000.0;             //  1/16!
+  pc = __fma_rn(pc, z, -1.0 / 87178291200.0);     // -1/14!
+  pc = __fma_rn(pc, z, 1.0 / 479001600.0);        //  1/12!
+  pc = __fma_rn(pc, z, -1.0 / 3628800.0);         // -1/10!
+  pc = __fma_rn(pc, z, 1.0 / 40320.0);            //  1/8!
+  pc = __fma_rn(pc, z, -1.0 / 720.0);             // -1/6!
+  pc = __fma_rn(pc, z, 1.0 / 24.0);               //  1/4!
+  pc = __fma_rn(pc, z, -0.5);                     // -1/2!
+  // sin x = x - x^3 * (1/6 - z/120 + ...) ;  cos x = 1 + z * pc
+  *s = __fma_rn(__dmul_rn(-x, z), ps, x);
+  *c = __fma_rn(z, pc, 1.0);
+}
 
 template <typename R, int NR>
 struct RealState {
@@ -46,6 +87,52 @@ __device__ __forceinline__ void store_real(const StateView& sv, int eid,
   for (int k = 0; k < NR; ++k) p[(int64_t)k * sv.n_envs] = s.v[k];
 }
 
+// Reset-ahead record of a RealState env: rec[e] = NR reals, contiguous (8 / 16 / 32 bytes).
+template <typename R, int NR>
+__device__ __forceinline__ void load_rec_real(const StateView& sv, int eid,
+                                              RealState<R, NR>& s) {
+  constexpr int kBytes = NR * (int)sizeof(R);
+  static_assert(kBytes == 8 || kBytes % 16 == 0, "record must be 8 bytes or 16-byte units");
+  const char* p = static_cast<const char*>(sv.rec) + (int64_t)eid * kBytes;
+  if constexpr (kBytes == 8) {
+    uint2 q = *reinterpret_cast<const uint2*>(p);
+    memcpy(&s.v[0], &q, 8);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kBytes / 16; ++i) {
+      uint4 q = reinterpret_cast<const uint4*>(p)[i];
+      memcpy(reinterpret_cast<char*>(&s.v[0]) + 16 * i, &q, 16);
+    }
+  }
+}
+template <typename R, int NR>
+__device__ __forceinline__ void store_rec_real(const StateView& sv, int eid,
+                                               const RealState<R, NR>& s) {
+  constexpr int kBytes = NR * (int)sizeof(R);
+  char* p = static_cast<char*>(sv.rec) + (int64_t)eid * kBytes;
+  if constexpr (kBytes == 8) {
+    uint2 q;
+    memcpy(&q, &s.v[0], 8);
+    *reinterpret_cast<uint2*>(p) = q;
+  } else {
+#pragma unroll
+    for (int i = 0; i < kBytes / 16; ++i) {
+      uint4 q;
+      memcpy(&q, reinterpret_cast<const char*>(&s.v[0]) + 16 * i, 16);
+      reinterpret_cast<uint4*>(p)[i] = q;
+    }
+  }
+}
+#define EPB_REC_RESET_MEMBERS                                                               \
+  static constexpr bool kRecReset = true;                                                   \
+  static __device__ __forceinline__ void load_rec(const StateView& sv, int e, State& s) {   \
+    load_rec_real(sv, e, s);                                                                \
+  }                                                                                         \
+  static __device__ __forceinline__ void store_rec(const StateView& sv, int e,              \
+                                                   const State& s) {                        \
+    store_rec_real(sv, e, s);                                                               \
+  }
+
 // ----------------------------------------------------------------------------- CartPole
 // cartpole.h:82-129
 template <typename R>
@@ -53,6 +140,7 @@ struct CartPole {
   using Act = int32_t;
   using State = RealState<R, 4>;  // x, x_dot, theta, theta_dot
   static constexpr bool kRngInReset = true, kRngInStep = false, kBlockObs = false;
+  EPB_REC_RESET_MEMBERS
   static __device__ __forceinline__ void load(const StateView& sv, int e, State& s) {
     load_real(sv, e, s);
   }
@@ -77,7 +165,7 @@ struct CartPole {
     done = (cur >= sv.max_steps);
     R force = act == 1 ? kForceMag : -kForceMag;
     R costheta, sintheta;
-    M<R>::sincos_(theta, &sintheta, &costheta);
+    M<R>::sincos_small_(theta, &sintheta, &costheta);
     R temp = (force + kMassPoleLength * theta_dot * theta_dot * sintheta) / kMassTotal;
     R theta_acc = (kGravity * sintheta - costheta * temp) /
                   (kLength * ((R)(4.0 / 3.0) - kMassPole * costheta * costheta / kMassTotal));
@@ -109,6 +197,7 @@ struct Pendulum {
   using Act = float;
   using State = RealState<R, 2>;  // theta, theta_dot
   static constexpr bool kRngInReset = true, kRngInStep = false, kBlockObs = false;
+  EPB_REC_RESET_MEMBERS
   static __device__ __forceinline__ void load(const StateView& sv, int e, State& s) {
     load_real(sv, e, s);
   }
@@ -172,6 +261,7 @@ struct Acrobot {
   using Act = int32_t;
   using State = RealState<R, 4>;  // s0..s3 (s4 = torque is transient)
   static constexpr bool kRngInReset = true, kRngInStep = false, kBlockObs = false;
+  EPB_REC_RESET_MEMBERS
   struct V5 { R s0, s1, s2, s3, s4; };
   static __device__ __forceinline__ V5 add(V5 a, V5 b) {
     return V5{a.s0 + b.s0, a.s1 + b.s1, a.s2 + b.s2, a.s3 + b.s3, a.s4 + b.s4};
@@ -264,6 +354,7 @@ struct MountainCar {
   using Act = typename std::conditional<kContinuous, float, int32_t>::type;
   using State = RealState<R, 2>;  // pos, vel
   static constexpr bool kRngInReset = true, kRngInStep = false, kBlockObs = false;
+  EPB_REC_RESET_MEMBERS
   static __device__ __forceinline__ void load(const StateView& sv, int e, State& s) {
     load_real(sv, e, s);
   }
@@ -334,6 +425,19 @@ launch_fn classic_step_fn(int kind, int precision) {
                        : launch_step<MountainCar<double, false>>;
     case 4: return f32 ? launch_step<MountainCar<float, true>>
                        : launch_step<MountainCar<double, true>>;
+  }
+  return nullptr;
+}
+launch_fn classic_refill_fn(int kind, int precision) {
+  bool f32 = precision == 1;
+  switch (kind) {
+    case 0: return f32 ? launch_refill<CartPole<float>> : launch_refill<CartPole<double>>;
+    case 1: return f32 ? launch_refill<Pendulum<float>> : launch_refill<Pendulum<double>>;
+    case 2: return f32 ? launch_refill<Acrobot<float>> : launch_refill<Acrobot<double>>;
+    case 3: return f32 ? launch_refill<MountainCar<float, false>>
+                       : launch_refill<MountainCar<double, false>>;
+    case 4: return f32 ? launch_refill<MountainCar<float, true>>
+                       : launch_refill<MountainCar<double, true>>;
   }
   return nullptr;
 }

@@ -14,6 +14,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "exchange.cuh"
 
 namespace epb {
@@ -33,6 +35,16 @@ struct StateView {
   int32_t* mt_idx;        // [N] index of the next word to regenerate, 0..623
   void* rstate;           // [NR][N] real state (double or float)
   int32_t* istate;        // [NI][N] integer state
+  // Reset-ahead records (envs whose Reset() is a pure function of their RNG stream:
+  // classic_control).  rec[e] always holds the env's NEXT initial state, drawn ahead of time
+  // by refill_kernel, so the step kernel's auto-reset is a load instead of a dependent
+  // mt19937 round trip on one lane of the warp.  The per-env draw ORDER is unchanged (these
+  // envs draw only at reset), so trajectories stay those of std::mt19937(seed + env_id).
+  void* rec;              // [N][NR] real, row per env (one or two 16-byte loads per lane)
+  uint8_t* rstat;         // [N] 1 = record full; rec_code = consumed, refill pending
+  int32_t rec_code;       // value a consuming step writes into rstat (2 | 3, step parity)
+  int32_t rec_spec;       // 1 = load the record with the state (L2-resident batch sizes),
+                          // 0 = only on the lanes that reset
 };
 
 // Output columns for one batch (pointers into a packed slab or caller arrays).
@@ -47,6 +59,7 @@ struct OutView {
   int32_t* step_type;    // step_type
   uint8_t* trunc;        // trunc
   void* env[5];          // env-specific keys in declaration order
+  int32_t* wire;         // sharded pools: packed common columns for the peers (exchange.cuh)
   int64_t t_stride_rows; // rollout: rows between consecutive time steps (= N)
 };
 
@@ -307,7 +320,9 @@ __device__ __forceinline__ void write_common(const OutView& ov, int64_t row, int
   if (ov.reward) ov.reward[row] = reward;
   if (ov.discount) ov.discount[row] = done ? 0.0f : 1.0f;
   if (ov.step_type) ov.step_type[row] = step_type;
-  if (ov.trunc) ov.trunc[row] = (uint8_t)(done && (cur >= max_steps));
+  const int trunc = done && (cur >= max_steps);
+  if (ov.trunc) ov.trunc[row] = (uint8_t)trunc;
+  if (ov.wire) ov.wire[row] = pack_wire(cur, done, trunc);
 }
 
 // Per-env result of one EnvStep, kept in registers until the output write.
@@ -327,29 +342,71 @@ struct StepOut {
 //   static constexpr bool kRngInReset, kRngInStep;  (Mt* is NULL when false)
 //   static constexpr bool kBlockObs;                (block-cooperative obs write)
 //
+// Envs with `static constexpr bool kRecReset = true` use the reset-ahead records.
+template <class Env, class = void>
+struct UsesRec { static constexpr bool value = false; };
+template <class Env>
+struct UsesRec<Env, typename std::enable_if<Env::kRecReset>::type> {
+  static constexpr bool value = true;
+};
+
 // One EnvStep (env.h:184-222) incl. the auto-reset decision (async_envpool.h:127).
+//
+// Reset, record envs: the state becomes the record (`rec`, already loaded when
+// sv.rec_spec), the record is marked consumed and refill_kernel draws the next one off the
+// critical path.  A record that is not full when it is needed is an engine invariant
+// violation (every consuming launch is followed by a refill before the same env can reset
+// again): trap, never step on with stale randomness.
+// Reset, other envs: the draws happen here (Mt, chunked table).
 template <class Env>
 __device__ __forceinline__ void env_step(const StateView& sv, int eid, int& flags,
                                          typename Env::State& s, typename Env::Act a,
-                                         bool force_reset, StepOut& so, int& mt_idx) {
+                                         bool force_reset, StepOut& so, int& mt_idx,
+                                         typename Env::State& rec, int& rstat) {
   int done = flags & 1;
   int cur = flags >> 1;
   const bool reset = force_reset || done;
-  // A warp usually holds both resetting and stepping lanes (CartPole: ~5 % of envs reset per
-  // step, so 80 % of warps do).  Order of work: resetting lanes ISSUE their mt19937 loads,
-  // then the stepping lanes run their arithmetic, then the resetting lanes consume the loads
-  // -- the memory latency of a reset hides behind the step math instead of adding to it.
-  Mt rng(sv, eid, mt_idx);
-  if (Env::kRngInReset && reset) rng.begin();
-  if (!reset) {
-    ++cur;
-    Env::step(sv, s, a, cur, done, Env::kRngInStep ? &rng : nullptr, so);
+  if constexpr (UsesRec<Env>::value) {
+    // Branch-free over `reset`: every lane runs the step arithmetic on the state it loaded
+    // (a warp almost always holds stepping lanes, so the resetting lanes ride along for
+    // free; a done env's stale state is finite, the result is discarded) and the resetting
+    // lanes then take their record.  With a branch, ptxas sinks the state loads into the
+    // step side -- behind the arrival of `flags`, one more dependent L2 round trip.
+    typename Env::State s1 = s;
+    StepOut so1 = so;
+    int cur1 = cur + 1, done1 = 0;
+    Env::step(sv, s1, a, cur1, done1, nullptr, so1);
+    if (reset) {
+      if (rstat < 0) {  // not loaded with the state: fetch it now (large batches)
+        rstat = sv.rstat[eid];
+        Env::load_rec(sv, eid, rec);
+      }
+      if (rstat != 1) __trap();
+      rstat = sv.rec_code;
+      sv.rstat[eid] = (uint8_t)rstat;
+    }
+    s = reset ? rec : s1;
+    so.reward = reset ? 0.0f : so1.reward;
+    so.extra = reset ? 0.0f : so1.extra;
+    cur = reset ? 0 : cur1;
+    done = reset ? 0 : done1;
   } else {
-    cur = 0;
-    done = 0;
-    Env::reset(sv, s, Env::kRngInReset ? &rng : nullptr, so);
+    // A warp usually holds both resetting and stepping lanes.  Order of work: resetting
+    // lanes ISSUE their mt19937 loads, then the stepping lanes run their arithmetic, then
+    // the resetting lanes consume the loads -- the memory latency of a reset hides behind
+    // the step math instead of adding to it.
+    Mt rng(sv, eid, mt_idx);
+    if (Env::kRngInReset && reset) rng.begin();
+    if (!reset) {
+      ++cur;
+      Env::step(sv, s, a, cur, done, Env::kRngInStep ? &rng : nullptr, so);
+    } else {
+      cur = 0;
+      done = 0;
+      Env::reset(sv, s, Env::kRngInReset ? &rng : nullptr, so);
+    }
+    if (Env::kRngInReset || Env::kRngInStep) mt_idx = rng.idx;
   }
-  if (Env::kRngInReset || Env::kRngInStep) mt_idx = rng.idx;
   flags = (cur << 1) | done;
 }
 
@@ -367,7 +424,8 @@ template <class Env, int kB = kBlock>
 __global__ void __launch_bounds__(kB)
 step_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ action,
             const int32_t* __restrict__ env_ids, int n, int force_reset,
-            const PeerView* __restrict__ peers) {
+            const PeerView* __restrict__ peers,
+            const typename Env::Act* __restrict__ next_action) {
   int row = blockIdx.x * kB + threadIdx.x;
   bool active = row < n;
   typename Env::State s;
@@ -376,27 +434,42 @@ step_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ acti
   so.extra = 0.f;
   int eid = 0, flags = 0;
   typename Env::Act a = typename Env::Act();
-  if (active) {
-    // inputs no earlier kernel of the stream writes: fetch them before the grid dependency
-    eid = env_ids ? env_ids[row] : row;
-    if (!force_reset) a = action[row];
-  }
   // Programmatic dependent launch: let the next step's grid start launching now, and wait
-  // here for the previous step's grid (it owns the state and the output slab until done).
-  // Both are no-ops when the kernel is launched without the PDL attribute.
+  // here for the previous kernel of the stream.  Every global load sits BEHIND the wait:
+  // the action / env_ids of the device-resident path are usually written by the kernel just
+  // before this one (a policy's argmax), and state and slab belong to the previous step.
+  // Both instructions are no-ops when the kernel is launched without the PDL attribute.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (active) {
     constexpr bool kRng = Env::kRngInReset || Env::kRngInStep;
+    constexpr bool kRec = UsesRec<Env>::value;
+    eid = env_ids ? env_ids[row] : row;
+    if (!force_reset) a = action[row];
     flags = sv.flags[eid];
-    int mt_idx = kRng ? sv.mt_idx[eid] : 0;
+    int mt_idx = 0, rstat = -1;
+    typename Env::State rec;
+    if constexpr (kRec) {
+      if (sv.rec_spec) {  // the record rides with the state loads: no dependent round trip
+        rstat = sv.rstat[eid];
+        Env::load_rec(sv, eid, rec);
+      }
+    } else if (kRng) {
+      mt_idx = sv.mt_idx[eid];
+    }
     const int mt_idx0 = mt_idx;
     Env::load(sv, eid, s);
+    // Step chains know the action row of the NEXT step: ask L2 for it now (one 128-byte line
+    // per warp, fire and forget).  The row is still read from HBM exactly once; what moves
+    // off the next kernel's critical path is the DRAM latency of its only cold input -- a
+    // policy that has just written the actions leaves them in L2 in the same way.
+    if (next_action && (threadIdx.x & 31) == 0)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(next_action + row));
     pin_value(a);
-    env_step<Env>(sv, eid, flags, s, a, force_reset != 0, so, mt_idx);
+    env_step<Env>(sv, eid, flags, s, a, force_reset != 0, so, mt_idx, rec, rstat);
     Env::store(sv, eid, s);
     sv.flags[eid] = flags;
-    if (kRng && mt_idx != mt_idx0) sv.mt_idx[eid] = mt_idx;
+    if (!kRec && kRng && mt_idx != mt_idx0) sv.mt_idx[eid] = mt_idx;
     write_common(ov, row, eid + sv.env_id_offset, flags >> 1, flags & 1, so.reward,
                  sv.max_steps);
   }
@@ -409,8 +482,30 @@ step_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ acti
   if (peers) peer_forward_rows<kB>(peers, (int64_t)blockIdx.x * kB, n);
 }
 
+// Draws the next initial state of every env whose record was consumed by the step with
+// `code` (0: every record that is not full -- pool creation, state import).  Runs BEHIND the
+// step that consumed and, in the engine's captured step chains, beside the next step (a
+// parallel graph branch): an env that resets at step t cannot reset again before t+2, which
+// waits for this kernel.  The only kernel that touches the mt19937 tables of record envs.
+template <class Env>
+__global__ void __launch_bounds__(kBlock) refill_kernel(StateView sv, int code) {
+  const int e = blockIdx.x * kBlock + threadIdx.x;
+  if (e >= sv.n_envs) return;
+  const int st = sv.rstat[e];
+  if (code ? st != code : st == 1) return;
+  Mt rng(sv, e);
+  typename Env::State s;
+  StepOut so;
+  Env::reset(sv, s, &rng, so);
+  Env::store_rec(sv, e, s);
+  rng.save(sv, e);
+  sv.rstat[e] = 1;
+}
+
 // Fused rollout: T sync steps of all N envs in one launch; state stays in registers, the
-// action stream [T,N] is read and the outputs [T,N,...] written once each.
+// action stream [T,N] is read and the outputs [T,N,...] written once each.  Record envs:
+// the first reset of an env takes its record, later ones draw in place, and the record is
+// redrawn before the kernel ends -- the draw order per env is the sequential one.
 template <class Env>
 __global__ void __launch_bounds__(kBlock)
 rollout_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ actions,
@@ -421,10 +516,18 @@ rollout_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ a
   typename Env::State s;
   int flags = 0, mt_idx = 0;
   constexpr bool kRng = Env::kRngInReset || Env::kRngInStep;
+  constexpr bool kRec = UsesRec<Env>::value;
+  typename Env::State rec;
+  bool have_rec = false;
   if (active) {
     flags = sv.flags[eid];
     if (kRng) mt_idx = sv.mt_idx[eid];
     Env::load(sv, eid, s);
+    if constexpr (kRec) {
+      if (sv.rstat[eid] != 1) __trap();
+      Env::load_rec(sv, eid, rec);
+      have_rec = true;
+    }
   }
   typename Env::Act a_next = typename Env::Act();
   if (active && T > 0) a_next = actions[eid];
@@ -436,7 +539,29 @@ rollout_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ a
     typename Env::Act a = a_next;
     if (active && t + 1 < T) a_next = actions[(int64_t)(t + 1) * n + eid];  // prefetch
     if (active) {
-      env_step<Env>(sv, eid, flags, s, a, false, so, mt_idx);
+      if constexpr (kRec) {
+        int done = flags & 1, cur = flags >> 1;
+        if (!done) {
+          ++cur;
+          Env::step(sv, s, a, cur, done, nullptr, so);
+        } else {
+          cur = 0;
+          done = 0;
+          if (have_rec) {
+            s = rec;
+            so.reward = 0.0f;
+            have_rec = false;
+          } else {
+            Mt rng(sv, eid, mt_idx);
+            Env::reset(sv, s, &rng, so);
+            mt_idx = rng.idx;
+          }
+        }
+        flags = (cur << 1) | done;
+      } else {
+        int rstat = 0;
+        env_step<Env>(sv, eid, flags, s, a, false, so, mt_idx, rec, rstat);
+      }
       write_common(ov, row, eid + sv.env_id_offset, flags >> 1, flags & 1, so.reward,
                    sv.max_steps);
     }
@@ -451,6 +576,15 @@ rollout_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ a
   if (active) {
     Env::store(sv, eid, s);
     sv.flags[eid] = flags;
+    if constexpr (kRec) {
+      if (!have_rec) {  // consumed: draw the next record now
+        Mt rng(sv, eid, mt_idx);
+        StepOut so;
+        Env::reset(sv, rec, &rng, so);
+        mt_idx = rng.idx;
+        Env::store_rec(sv, eid, rec);
+      }
+    }
     if (kRng) sv.mt_idx[eid] = mt_idx;
   }
 }
@@ -466,6 +600,8 @@ struct LaunchArgs {
   int T;  // rollout only
   cudaStream_t stream;
   const PeerView* peers;  // device pointer; non-NULL = fused peer exchange epilogue
+  const void* next_action;  // step chains: action row of the following step (L2 prefetch)
+  int refill_code;        // refill only: rstat value to match (0 = every record not full)
 };
 typedef cudaError_t (*launch_fn)(const LaunchArgs&);
 
@@ -506,10 +642,16 @@ cudaError_t launch_step_b(const LaunchArgs& a) {
   // (5.9 vs 5.0 us/step, CartPole N=65536), so captures keep full serialisation.
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(a.stream, &cap);
-  cfg.numAttrs = (pdl_enabled() && cap == cudaStreamCaptureStatusNone) ? 1 : 0;
+  static const bool pdl_in_graph = [] {
+    const char* e = getenv("ENVPOOL_B200_PDL_GRAPH");
+    return e && e[0] == '1';
+  }();
+  cfg.numAttrs =
+      (pdl_enabled() && (cap == cudaStreamCaptureStatusNone || pdl_in_graph)) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, step_kernel<Env, kB>, a.sv, a.ov,
                             static_cast<const typename Env::Act*>(a.action), a.env_ids, a.n,
-                            a.force_reset, a.peers);
+                            a.force_reset, a.peers,
+                            static_cast<const typename Env::Act*>(a.next_action));
 }
 
 template <class Env>
@@ -528,8 +670,16 @@ cudaError_t launch_rollout(const LaunchArgs& a) {
   return cudaGetLastError();
 }
 
+template <class Env>
+cudaError_t launch_refill(const LaunchArgs& a) {
+  int grid = (a.sv.n_envs + kBlock - 1) / kBlock;
+  refill_kernel<Env><<<grid, kBlock, 0, a.stream>>>(a.sv, a.refill_code);
+  return cudaGetLastError();
+}
+
 // family entry points (classic.cu / toytext.cu / mujoco.cu)
 launch_fn classic_step_fn(int kind, int precision);
+launch_fn classic_refill_fn(int kind, int precision);
 launch_fn classic_rollout_fn(int kind, int precision);
 launch_fn toytext_step_fn(int kind, int iopt);
 launch_fn toytext_rollout_fn(int kind, int iopt);

@@ -3,23 +3,35 @@
 // The reference has no counterpart (it is single-process); north_star asks that after every
 // step each GPU holds the outputs of ALL envs.  Every rank owns one "gather" allocation
 //
-//     gather[2][world][slab_bytes] | flags[world] (u64) | ctl {blocks_done, seq, error}
+//     slot[D][world][slice_bytes] | data_flag[16] | ack_flag[16] | ctl | PeerView[D]
 //
 // mapped into every peer (CUDA IPC between processes, plain pointers inside one process).
-// A step writes its packed output slab straight into gather[parity][rank] of the LOCAL
-// allocation (no staging copy) and the same bytes go into gather[parity][rank] of every peer
-// over NVLink with 16-byte stores, after which the step's sequence number is published in
-// flags[rank] of every rank with a system-scope release.  Two producers of the peer stores:
+// slice = the packed output slab (all 13 columns at their slab offsets) + one extra "wire"
+// column `packed[N]` (int32: elapsed_step << 2 | trunc << 1 | done).
+//
+// What crosses NVLink per env-step is only what a peer cannot know: the env keys (obs and
+// info columns), `reward` and the packed word -- CartPole 24 B instead of the slab's 42 B.
+// info:env_id / info:players.env_id are constants (written into every slot once, at attach
+// time); elapsed_step, done, trunc, discount and step_type are re-expanded from the packed
+// word on the receiving GPU (`wait_derive_kernel`), where the bytes cost local HBM, not link.
+//
+// A step writes its slab straight into slot[t % D][rank] of the LOCAL allocation (no staging
+// copy) and the wire columns go into slot[t % D][rank] of every peer with 16-byte stores,
+// after which the step's sequence number is published in data_flag[rank] of every rank.
+// Producers of the peer stores:
 //   * fused (classic_control / toy_text): the step kernel's own epilogue -- each CTA forwards
 //     the rows it has just written (`peer_forward_rows`), so the transfer rides inside the
-//     step launch and no second kernel sits on the critical path;
+//     step launch;
 //   * `push_kernel` (HalfCheetah, or ENVPOOL_B200_EXCHANGE=push): a copy kernel behind the
 //     step kernel (capi.cu).
-// `wait_kernel` (one warp, capi.cu) acquires flags[0..world) >= seq before the consumer of
-// the gathered batch runs.  The two parities make step t+1's stores land in the other half
-// while step t is still being consumed: a peer cannot start pushing step t+2 before it has
-// seen this rank's flag for t+1, which this rank raises only after (stream order) its consumer
-// of step t -- so no acknowledgement traffic is needed.
+// Flow control.  D slots form a ring, so a rank may run up to D-1 steps ahead of the slowest
+// consumer: step t+1 computes and pushes while the data of step t is still in flight or being
+// consumed (the sender never waits for the transfer of the previous step).  Slot t % D may be
+// overwritten by step t + D only after every rank has released step t; a rank releases by
+// publishing ack_flag (its wait kernel for step u first stores "steps < u are consumed" into
+// ack_flag[rank] of every rank).  `credit_kernel` (one warp, in front of step t) holds the
+// stream until every ack >= t - D + 1.  With step/wait strictly alternating on one stream
+// the credit is always there already.
 //
 // Why not ncclAllGather: measured 35 us per call for the 2.75 MB CartPole slab on 2 GPUs
 // (protocol latency), against ~4 us for the step itself; the peer stores cost the NVLink time
@@ -31,24 +43,26 @@
 namespace epb {
 
 constexpr int kMaxPeers = 16;
+constexpr int kMaxDepth = 8;
 
 constexpr int kMaxCols = 13;  // 8 common state keys + at most 5 env keys (OutView::env)
 
 struct ExchangeCtl {
-  unsigned int blocks_done;
-  unsigned int pad;
-  unsigned long long seq;   // steps pushed by this rank
-  int error;                // 1 = a wait timed out
+  unsigned int blocks_done;    // last-block-done counter of the publishing kernel
+  unsigned int wait_blocks;    // ... and of the wait kernel
+  unsigned long long seq;      // steps pushed by this rank
+  unsigned long long waited;   // steps whose wait kernel has finished on this rank
+  int error;                   // 1 = a wait timed out
   int pad2;
 };
 
 struct PeerView {
-  char* slice[kMaxPeers];                // gather[parity][rank] in the allocation of rank g
-  unsigned long long* flag[kMaxPeers];   // &flags[rank] in the allocation of rank g
+  char* slice[kMaxPeers];                // slot[s][rank] in the allocation of rank g
+  unsigned long long* flag[kMaxPeers];   // &data_flag[rank] in the allocation of rank g
   ExchangeCtl* ctl;                      // this rank's control block
   int world;
   int rank;
-  // packed-slab columns (fused epilogue): byte offset in the slab and bytes per row
+  // wire columns (forwarded to peers): byte offset in the slice and bytes per row
   int ncols;
   int col_rb[kMaxCols];
   int64_t col_off[kMaxCols];
@@ -67,9 +81,14 @@ __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned l
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// elapsed_step << 2 | trunc << 1 | done: everything the common columns are made of
+__device__ __forceinline__ int32_t pack_wire(int cur, int done, int trunc) {
+  return (cur << 2) | (trunc << 1) | done;
+}
+
 // Last-block-done publication: every CTA fences its peer stores at system scope before it
 // counts itself; the CTA that completes the count bumps the sequence number and raises
-// flags[rank] on every rank -- ONE system fence, then relaxed flag stores (a release per
+// data_flag[rank] on every rank -- ONE system fence, then relaxed flag stores (a release per
 // flag would pay one NVLink round trip per peer).  Call with all threads of the CTA.
 __device__ __forceinline__ void peer_publish(const PeerView* __restrict__ pv) {
   __threadfence_system();
@@ -88,9 +107,9 @@ __device__ __forceinline__ void peer_publish(const PeerView* __restrict__ pv) {
   }
 }
 
-// Fused epilogue of the step kernels: the CTA forwards the output rows [row0, row0 + kB)
-// it has just written into its local gather slice to every peer, then publishes.  The rows
-// of all columns are treated as one list of 16-byte units (column k contributes
+// Fused epilogue of the step kernels: the CTA forwards the wire columns of the output rows
+// [row0, row0 + kB) it has just written into its local slice to every peer, then publishes.
+// The rows of all wire columns are treated as one list of 16-byte units (column k contributes
 // ceil(rows * row_bytes / 16) of them); each thread loads up to four units before it issues
 // any peer store, so the L2 read latency is paid once, not once per column.  Requires the
 // identity row<->env mapping (sync step of all envs) and kB % 16 == 0, so that every
@@ -101,7 +120,7 @@ __device__ __forceinline__ void peer_forward_rows(const PeerView* __restrict__ p
                                                   int n) {
   static_assert(kB % 16 == 0, "CTA rows must keep 1-byte columns 16-byte aligned");
   __shared__ int s_first[kMaxCols + 1];   // first unit of column k in this CTA's unit list
-  __shared__ int64_t s_off[kMaxCols];     // slab byte offset of this CTA's rows in column k
+  __shared__ int64_t s_off[kMaxCols];     // slice byte offset of this CTA's rows in column k
   __shared__ char* s_peer[kMaxPeers];
   const int64_t left = (int64_t)n - row0;
   const int rows = left < kB ? (int)left : kB;

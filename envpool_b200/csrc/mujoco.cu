@@ -715,17 +715,20 @@ hc_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict__ act
       const double x_before = w.q[0];
       for (int k = 0; k < prm.frame_skip; ++k) hc_substep(w, lane);
       x_after = w.q[0];
-      for (int k = 0; k < NU; ++k) ctrl_cost += prm.ctrl_cost_weight * w.ctrl[k] * w.ctrl[k];
+      // env-layer algebra (half_cheetah.h:147-160) with explicit _rn ops: never FMA-contracted,
+      // so reward / infos are the x86-64 double results given the same qpos, ctrl
+      for (int k = 0; k < NU; ++k)
+        ctrl_cost = __dadd_rn(ctrl_cost, __dmul_rn(__dmul_rn(prm.ctrl_cost_weight, w.ctrl[k]), w.ctrl[k]));
       const double dt = prm.frame_skip * cm.timestep;
       xv = (x_after - x_before) / dt;
-      reward = (float)(xv * prm.forward_reward_weight - ctrl_cost);
+      reward = (float)__dsub_rn(__dmul_rn(xv, prm.forward_reward_weight), ctrl_cost);
       done = (cur >= sv.max_steps);
     }
     flags = (cur << 1) | done;
     if (lane == 0) {
       write_common(ov, orow, eid + sv.env_id_offset, cur, done, reward, sv.max_steps);
       // infos (half_cheetah.h:178-181); on reset WriteState gets literal zeros
-      if (ov.env[1]) static_cast<double*>(ov.env[1])[orow] = xv * prm.forward_reward_weight;
+      if (ov.env[1]) static_cast<double*>(ov.env[1])[orow] = __dmul_rn(xv, prm.forward_reward_weight);
       if (ov.env[2]) static_cast<double*>(ov.env[2])[orow] = -ctrl_cost;
       if (ov.env[3]) static_cast<double*>(ov.env[3])[orow] = x_after;
       if (ov.env[4]) static_cast<double*>(ov.env[4])[orow] = xv;
@@ -802,15 +805,18 @@ hc_thread_kernel(StateView sv, OutView ov, HcParams prm, const double* __restric
       for (int k = 0; k < prm.frame_skip; ++k) hct::substep(s, e);
       x_after = s.q[0];
 #pragma unroll
-      for (int k = 0; k < NU; ++k) ctrl_cost += prm.ctrl_cost_weight * s.ctrl[k] * s.ctrl[k];
+      // env-layer algebra (half_cheetah.h:147-160) with explicit _rn ops: never FMA-contracted,
+      // so reward / infos are the x86-64 double results given the same qpos, ctrl
+      for (int k = 0; k < NU; ++k)
+        ctrl_cost = __dadd_rn(ctrl_cost, __dmul_rn(__dmul_rn(prm.ctrl_cost_weight, s.ctrl[k]), s.ctrl[k]));
       const double dt = prm.frame_skip * cm.timestep;
       xv = (x_after - x_before) / dt;
-      reward = (float)(xv * prm.forward_reward_weight - ctrl_cost);
+      reward = (float)__dsub_rn(__dmul_rn(xv, prm.forward_reward_weight), ctrl_cost);
       done = (cur >= sv.max_steps);
     }
     flags = (cur << 1) | done;
     write_common(ov, orow, eid + sv.env_id_offset, cur, done, reward, sv.max_steps);
-    if (ov.env[1]) static_cast<double*>(ov.env[1])[orow] = xv * prm.forward_reward_weight;
+    if (ov.env[1]) static_cast<double*>(ov.env[1])[orow] = __dmul_rn(xv, prm.forward_reward_weight);
     if (ov.env[2]) static_cast<double*>(ov.env[2])[orow] = -ctrl_cost;
     if (ov.env[3]) static_cast<double*>(ov.env[3])[orow] = x_after;
     if (ov.env[4]) static_cast<double*>(ov.env[4])[orow] = xv;

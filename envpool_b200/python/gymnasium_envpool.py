@@ -2,7 +2,10 @@
 `(obs, info)`, `step()` / `recv()` give `(obs, reward, terminated, truncated, info)`."""
 from __future__ import annotations
 
+import warnings
 from abc import ABCMeta
+
+import numpy as np
 
 from .adapter import build_adapter
 from .data import fill_tree, gym_structure
@@ -34,6 +37,39 @@ class GymnasiumEnvPoolMixin:
     @property
     def num_envs(self):
         return self.config["num_envs"]
+
+    # what gymnasium wrappers / SB3 probe on a vector env
+    # (envpool/python/gymnasium_envpool.py:79-97)
+    metadata = {"render_modes": ["rgb_array", "human"], "autoreset_mode": "next_step"}
+    is_vector_env = True
+    render_mode = None
+
+    def reset(self, env_id=None, *, seed=None, options=None):
+        """gymnasium's keyword form (envpool/python/gymnasium_envpool.py:129-153): `seed`
+        cannot re-seed a pool (seeds are fixed by make()) and is ignored with a warning;
+        options may only carry `reset_mask`, a bool[num_envs] choosing the envs to reset."""
+        if seed is not None:
+            warnings.warn("envpool_b200 fixes every env's seed at make(); reset(seed=...) is "
+                          "ignored -- pass seed to make() instead.", stacklevel=2)
+        if options:
+            extra = sorted(set(options) - {"reset_mask"})
+            if extra:
+                raise ValueError(f"unsupported reset options: {extra}")
+            mask = options.get("reset_mask")
+            if mask is not None:
+                if env_id is not None:
+                    raise ValueError("give either env_id or options['reset_mask'], not both")
+                mask = np.asarray(mask, dtype=np.bool_)
+                n = self.config["num_envs"]
+                if mask.shape != (n,):
+                    raise ValueError(f"reset_mask must have shape ({n},), got {mask.shape}")
+                if not mask.any():
+                    raise ValueError("reset_mask selects no environment")
+                env_id = np.flatnonzero(mask).astype(np.int32)
+        return super().reset(env_id)
+
+    def close(self, **kwargs):
+        return super().close()
 
 
 def _five_tuple_fold(state_keys):

@@ -7,9 +7,10 @@ do not depend on G.  The one exchange step of the path is an all-gather of the o
 columns, which reassembles the full `[num_envs, ...]` batch on every rank.  Two transports:
 
 * the engine's own peer exchange (csrc/exchange.cuh): the step writes into this rank's slice
-  of a gather buffer that every peer maps through CUDA IPC, a push kernel stores the slice
-  into all peers over NVLink and raises sequence flags -- `enable_peer_exchange()`,
-  `reset_exchange()`, `step_exchange(actions)`;
+  of a ring of gather slots that every peer maps through CUDA IPC, its epilogue stores the
+  columns a peer cannot derive (env keys, reward, one packed word) into all peers over
+  NVLink and raises sequence flags; the receiver re-expands the rest --
+  `enable_peer_exchange()`, `reset_exchange()`, `step_exchange(actions)`;
 * `torch.distributed` all-gather (NCCL on GPUs; gloo on CPU tensors in the host-logic
   tests) -- `all_gather()`; also the cross-check of the first.
 
@@ -178,12 +179,12 @@ class ShardedPool:
         from ._capi import _torch_view
 
         ptr = self.pool.exchange_wait()
-        full = _torch_view(ptr, (self.world, self.pool.slab_bytes), torch.uint8,
+        full = _torch_view(ptr, (self.world, self.pool.exchange_slice_bytes), torch.uint8,
                            self.pool.device)
         return packed_views(full, self.pool.keys, self.count)
 
     def reset_exchange(self):
-        """Forced reset of all local envs + exchange; views valid until the second-next call."""
+        """Forced reset of all local envs + exchange; views valid until the next call."""
         self.pool.step_exchange(None)
         return self._gathered()
 

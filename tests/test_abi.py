@@ -19,7 +19,7 @@ def test_engine_builds_and_exports_all_declared_symbols(engine_built):
     lib = ctypes.CDLL(_capi.ENGINE_SO)
     for sym in sorted(declared):
         assert hasattr(lib, sym), f"missing export {sym}"
-    assert lib.epb_abi_version() == 1
+    assert lib.epb_abi_version() == 2
 
 
 def test_engine_is_sm_100a_sass():

@@ -17,7 +17,7 @@ def _views(pool, ptr, world, n_local):
     from envpool_b200._capi import _torch_view
     from envpool_b200.sharded import packed_views
 
-    full = _torch_view(ptr, (world, pool.slab_bytes), torch.uint8, pool.device)
+    full = _torch_view(ptr, (world, pool.exchange_slice_bytes), torch.uint8, pool.device)
     return packed_views(full, pool.keys, n_local)
 
 
@@ -67,6 +67,67 @@ def test_two_ranks_one_device(task, kw, n_act):
         p.close()
 
 
+@pytest.mark.parametrize("task,kw,n_act,tol", [
+    ("CartPole", dict(max_episode_steps=9), 2, 1e-6),
+    ("Catch", dict(), 3, 0.0),
+])
+def test_captured_exchange_chain_runs_ahead_of_the_waits(task, kw, n_act, tol):
+    """epb_step_exchange_many_device: K exchanged steps in one CUDA graph, the waits on a
+    parallel branch, so step t+1..t+depth-2 compute and push while the batch of step t is
+    still arriving (ring slots + credit / ack flags).  After every chain both ranks hold the
+    oracle's full batch; the un-captured chain gives the same bytes."""
+    import torch
+
+    from envpool_b200._capi import CPool
+    from oracle.oracle_lib import OraclePool
+
+    n, world, T = 3000, 2, 24
+    rng = np.random.default_rng(4)
+    acts = rng.integers(0, n_act, size=(T, world * n)).astype(np.int32)
+    d_acts = [torch.from_numpy(np.ascontiguousarray(acts[:, r * n:(r + 1) * n])).cuda()
+              for r in range(world)]
+
+    def make():
+        pools = [CPool(task, n, seed=3, env_id_offset=r * n, **kw) for r in range(world)]
+        for r, p in enumerate(pools):
+            p.exchange_init(world, r)
+        bases = [p.exchange_base() for p in pools]
+        for p in pools:
+            p.exchange_attach(bases)
+        for p in pools:
+            p.step_exchange(None)
+        for p in pools:
+            p.exchange_wait()
+        return pools
+
+    pools, plain = make(), make()
+    orc = OraclePool(task, world * n, seed=3, **kw)
+    orc.reset()
+    assert pools[0].exchange_depth >= 3
+    t = 0
+    for K in (8, 8, 4, 12, 8):
+        ptrs = [p.step_exchange_many(d_acts[r], t % T, K, use_graph=True)
+                for r, p in enumerate(pools)]
+        ptrs2 = [p.step_exchange_many(d_acts[r], t % T, K, use_graph=False)
+                 for r, p in enumerate(plain)]
+        for k in range(K):
+            want = orc.step(acts[(t + k) % T])
+        t += K
+        for p in pools + plain:
+            p.sync()
+        for r, p in enumerate(pools):
+            got = {k: v.reshape((world * n,) + tuple(v.shape[2:])).cpu().numpy()
+                   for k, v in _views(p, ptrs[r], world, n).items()}
+            assert_batch_equal(got, want, task, tol, f"{task} rank {r} after {t} steps")
+            got2 = {k: v.reshape((world * n,) + tuple(v.shape[2:])).cpu().numpy()
+                    for k, v in _views(plain[r], ptrs2[r], world, n).items()}
+            assert_batch_equal(got2, got, task, 0.0, f"{task} rank {r}: direct vs captured")
+    for p in pools + plain:
+        steps, timed_out = p.exchange_status()
+        assert steps == 1 + t and not timed_out
+        p.close()
+
+
 def test_exchange_errors_and_single_rank():
     import torch
 
@@ -101,5 +162,16 @@ def test_exchange_errors_and_single_rank():
         got = _views(q, ptr, 1, 64)
         for k, v in ref.outputs_torch().items():
             assert torch.equal(got[k][0], v), k
+    # flow control: at most depth - 1 exchanged steps may be outstanding
+    for _ in range(q.exchange_depth - 1):
+        q.step_exchange(a)
+    with pytest.raises(EpbError):
+        q.step_exchange(a)
+    for _ in range(q.exchange_depth - 1):
+        q.exchange_wait()
+    with pytest.raises(EpbError):
+        q.exchange_wait()
+    q.sync()
+    assert q.exchange_status() == (5 + q.exchange_depth - 1, False)
     q.close()
     ref.close()

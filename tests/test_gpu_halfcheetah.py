@@ -15,16 +15,6 @@ KEYS_EXACT = ("info:env_id", "info:players.env_id", "elapsed_step", "done", "dis
               "step_type", "trunc")
 
 
-@pytest.fixture(scope="module")
-def capi(engine_built):
-    import torch
-
-    assert torch.cuda.is_available()
-    from envpool_b200 import _capi
-
-    return _capi
-
-
 def _relerr(g, w):
     return np.abs(g - w) / (1 + np.abs(w))
 

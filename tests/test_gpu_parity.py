@@ -21,17 +21,6 @@ CLASSIC = ["CartPole", "Pendulum", "Acrobot", "MountainCar", "MountainCarContinu
 TOY = ["FrozenLake", "Catch", "Taxi", "NChain", "CliffWalking", "Blackjack"]
 
 
-@pytest.fixture(scope="module")
-def capi(engine_built):
-    import torch
-
-    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
-    from envpool_b200 import _capi
-
-    _capi.load_library()
-    return _capi
-
-
 @pytest.mark.parametrize("case", golden_cases())
 def test_golden_trajectories_host_path(capi, case):
     meta, gold = load_golden(case)
@@ -216,20 +205,25 @@ def test_env_seed_list_and_errors(capi):
         pool.recv()                                       # nothing outstanding
 
 
-def test_snapshot_roundtrip(capi):
+@pytest.mark.parametrize("task", ["FrozenLake", "CartPole", "Pendulum"])
+def test_snapshot_roundtrip(capi, task):
+    """The state blob is the whole env state (classic_control: the reset-ahead records
+    travel with it)."""
     N = 1000
+    ms, iopt = REGISTERED[task]
+    ms = min(ms, 30)   # several resets inside the compared window
     rng = np.random.default_rng(8)
-    a = capi.CPool("FrozenLake", N, seed=2, max_episode_steps=100, iopt=4)
+    a = capi.CPool(task, N, seed=2, max_episode_steps=ms, iopt=iopt)
     a.reset()
     for _ in range(20):
-        a.step(random_actions("FrozenLake", rng, (N,)))
+        a.step(random_actions(task, rng, (N,)))
     blob = a.state_export()
-    acts = random_actions("FrozenLake", rng, (25, N))
-    want = [a.step(acts[t]) for t in range(25)]
-    b = capi.CPool("FrozenLake", N, seed=999, max_episode_steps=100, iopt=4)
+    acts = random_actions(task, rng, (45, N))
+    want = [a.step(acts[t]) for t in range(45)]
+    b = capi.CPool(task, N, seed=999, max_episode_steps=ms, iopt=iopt)
     b.state_import(blob)
-    for t in range(25):
-        assert_batch_equal(b.step(acts[t]), want[t], "FrozenLake", 0.0, f"snapshot t={t}")
+    for t in range(45):
+        assert_batch_equal(b.step(acts[t]), want[t], task, 0.0, f"snapshot t={t}")
 
 
 # ---- BASELINE.json full sizes: size-independent properties -------------------------------
