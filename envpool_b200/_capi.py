@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "epb_bytes_per_env_step", "epb_exchange_init", "epb_exchange_base", "epb_exchange_attach",
     "epb_exchange_attach_ipc", "epb_step_exchange_device", "epb_exchange_wait",
     "epb_exchange_status", "epb_exchange_slice_bytes", "epb_exchange_depth",
-    "epb_step_many_timed", "epb_step_exchange_many_device",
+    "epb_step_many_timed", "epb_step_exchange_many_device", "epb_fp64_peak_gflops",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -121,12 +121,20 @@ def load_library() -> ctypes.CDLL:
     L.epb_step_many_timed.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, vp,
                                       ctypes.POINTER(ctypes.c_float)]
     L.epb_step_exchange_many_device.argtypes = [vp, vp, ci, ci, ci, ci, vp, pp]
+    L.epb_fp64_peak_gflops.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
     _lib = L
     return L
 
 
 class EpbError(RuntimeError):
     pass
+
+
+def fp64_peak_gflops(device: int = 0) -> float:
+    """Sustained fp64 FMA rate of the device (GFLOP/s), measured by the engine."""
+    out = ctypes.c_double()
+    _check(load_library().epb_fp64_peak_gflops(device, ctypes.byref(out)))
+    return float(out.value)
 
 
 def _check(rc: int):

@@ -129,6 +129,9 @@ struct epb_pool {
   std::vector<std::pair<void*, int>> leases;  // slab -> outstanding recv leases + queue refs
   std::vector<void*> free_slabs;
   std::vector<void*> all_slabs;
+  // pinned slabs whose two id columns hold arange + env_id_offset (the full sync batch with
+  // identity ids never changes them, so its D2H copy skips them)
+  std::vector<void*> ids_ok_slabs;
   std::deque<Pending> pending;
   std::vector<cudaEvent_t> free_events;
   std::mutex mu;
@@ -139,6 +142,7 @@ struct epb_pool {
   // parallel branch of the engine's captured step chains
   launch_fn refill_fn = nullptr;
   uint64_t seq = 0;
+  int last_code = 0;  // consume code of the most recent step launch
   cudaStream_t side = nullptr;
   cudaEvent_t ev_step[2] = {nullptr, nullptr}, ev_refill[2] = {nullptr, nullptr};
   MjcPool* mjc = nullptr;
@@ -272,19 +276,50 @@ int build_keys(epb_pool* p) {
   return 0;
 }
 
-int get_slab(epb_pool* p, void** out) {
+void fill_id_columns(epb_pool* p, void* slab) {
+  int32_t* a = reinterpret_cast<int32_t*>(static_cast<char*>(slab) + p->keys[0].off);
+  int32_t* b = reinterpret_cast<int32_t*>(static_cast<char*>(slab) + p->keys[1].off);
+  const int off = p->cfg.env_id_offset;
+  for (int i = 0; i < p->N; ++i) a[i] = b[i] = off + i;
+}
+
+int alloc_slab(epb_pool* p, void** out) {
+  void* h = nullptr;
+  cudaError_t e = cudaHostAlloc(&h, (size_t)p->slab_bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess)
+    return fail(EPB_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  fill_id_columns(p, h);
+  p->all_slabs.push_back(h);
+  p->ids_ok_slabs.push_back(h);
+  *out = h;
+  return EPB_OK;
+}
+
+// A free pinned slab (recycled; a new one costs milliseconds of cudaHostAlloc, which is why
+// epb_create allocates the first few).  *ids_ok: its id columns already hold the identity.
+int get_slab(epb_pool* p, void** out, bool* ids_ok) {
   std::lock_guard<std::mutex> lk(p->mu);
   if (!p->free_slabs.empty()) {
     *out = p->free_slabs.back();
     p->free_slabs.pop_back();
-    return EPB_OK;
+  } else {
+    int rc = alloc_slab(p, out);
+    if (rc != EPB_OK) return rc;
   }
-  void* h = nullptr;
-  cudaError_t e = cudaHostAlloc(&h, (size_t)p->slab_bytes, cudaHostAllocDefault);
-  if (e != cudaSuccess) return fail(EPB_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
-  p->all_slabs.push_back(h);
-  *out = h;
+  *ids_ok = false;
+  for (void* s : p->ids_ok_slabs)
+    if (s == *out) *ids_ok = true;
   return EPB_OK;
+}
+void set_ids_ok(epb_pool* p, void* slab, bool ok) {
+  std::lock_guard<std::mutex> lk(p->mu);
+  for (size_t i = 0; i < p->ids_ok_slabs.size(); ++i)
+    if (p->ids_ok_slabs[i] == slab) {
+      if (ok) return;
+      p->ids_ok_slabs.erase(p->ids_ok_slabs.begin() + i);
+      return;
+    }
+  if (ok) p->ids_ok_slabs.push_back(slab);
 }
 
 int get_event(epb_pool* p, cudaEvent_t* ev) {
@@ -521,7 +556,8 @@ int launch_batch(epb_pool* p, const void* d_action, const int32_t* d_ids, int n,
   EPB_CUDA(p->step_fn(a));
   ++p->launches;
   ++p->seq;
-  if (p->refill_fn) {
+  p->last_code = code;
+  if (p->refill_fn && chain_k != -2 && !(p->sv.rec_spec & 2)) {
     if (chain_k < 0) return launch_refill(p, code, stream);
     const int h = chain_k & 1;
     EPB_CUDA(cudaEventRecord(p->ev_step[h], stream));
@@ -578,15 +614,27 @@ int host_submit(epb_pool* p, const void* action, const int32_t* env_ids, int n,
                              p->stream));
   }
   EPB_CUDA(cudaEventRecord(p->h_stage_ev[f], p->stream));
-  int rc = launch_batch(p, p->d_action, d_ids, n, force_reset, p->d_slab, p->stream);
+  // the step kernel alone; the refill of the records it consumed goes BEHIND the D2H copy
+  // (the caller waits for the copy, not for the refill)
+  int rc = launch_batch(p, p->d_action, d_ids, n, force_reset, p->d_slab, p->stream, nullptr,
+                        -2);
   if (rc != EPB_OK) return rc;
   void* slab = nullptr;
-  rc = get_slab(p, &slab);
+  bool ids_ok = false;
+  rc = get_slab(p, &slab, &ids_ok);
   if (rc != EPB_OK) return rc;
-  if (n == p->N) {
-    EPB_CUDA(cudaMemcpyAsync(slab, p->d_slab, (size_t)p->slab_bytes, cudaMemcpyDeviceToHost,
+  if (n == p->N && identity) {
+    // the id columns of a full identity batch are constants the pinned slab already holds
+    if (!ids_ok) {
+      fill_id_columns(p, slab);
+      set_ids_ok(p, slab, true);
+    }
+    const int64_t from = p->keys[2].off;
+    EPB_CUDA(cudaMemcpyAsync(static_cast<char*>(slab) + from, p->d_slab + from,
+                             (size_t)(p->slab_bytes - from), cudaMemcpyDeviceToHost,
                              p->stream));
   } else {
+    if (ids_ok) set_ids_ok(p, slab, false);
     for (const Key& k : p->keys) {
       EPB_CUDA(cudaMemcpyAsync(static_cast<char*>(slab) + k.off, p->d_slab + k.off,
                                (size_t)k.row_bytes * n, cudaMemcpyDeviceToHost, p->stream));
@@ -601,6 +649,7 @@ int host_submit(epb_pool* p, const void* action, const int32_t* env_ids, int n,
     p->pending.push_back(Pending{slab, n, 0, ev, false});
     p->leases.emplace_back(slab, 1);  // the queue's own reference
   }
+  if (p->refill_fn && !(p->sv.rec_spec & 2)) return launch_refill(p, p->last_code, p->stream);
   return EPB_OK;
 }
 
@@ -706,6 +755,22 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
   p->batch = cfg->batch_size > 0 ? cfg->batch_size : p->N;
   p->arange.resize(p->N);
   for (int i = 0; i < p->N; ++i) p->arange[i] = i;
+  {
+    // the first pinned slabs now (cudaHostAlloc costs milliseconds: never inside a step):
+    // a sync loop holds two (the batch the caller reads + the one in flight), a pipelined or
+    // async one a third; capped at 1 GiB of pinned memory
+    int want = (int)((int64_t(1) << 30) / (p->slab_bytes > 0 ? p->slab_bytes : 1));
+    want = want > 3 ? 3 : (want < 1 ? 1 : want);
+    for (int i = 0; i < want; ++i) {
+      void* h = nullptr;
+      if (alloc_slab(p, &h) != EPB_OK) {
+        std::string msg = g_err;
+        epb_destroy(p);
+        return fail(EPB_ERR_CUDA, msg);
+      }
+      p->free_slabs.push_back(h);
+    }
+  }
   char* blob = static_cast<char*>(p->d_state_blob);
   p->sv.n_envs = p->N;
   p->sv.max_steps = cfg->max_episode_steps > 0 ? cfg->max_episode_steps : INT_MAX;
@@ -721,8 +786,13 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
     p->sv.rstat = reinterpret_cast<uint8_t*>(blob + o_rstat);
     // Load the record with the state while state + records + slab stay L2-resident; for
     // larger batches only the resetting lanes fetch it.  ENVPOOL_B200_REC_SPEC=0|1 overrides.
-    p->sv.rec_spec = N <= 262144 ? 1 : 0;
+    // Measured (profiles/r2_step_ab.md): with the conditional load issued ahead of the step
+    // arithmetic the two variants are within noise at 65536 envs and the conditional one wins
+    // above L2 size, so it is the default; ENVPOOL_B200_REC_SPEC=1 selects the speculative load.
+    p->sv.rec_spec = 0;
     if (const char* rs = getenv("ENVPOOL_B200_REC_SPEC")) p->sv.rec_spec = rs[0] == '1';
+    if (const char* nr = getenv("ENVPOOL_B200_NO_REFILL"))  // timing experiment, wrong results
+      if (nr[0] == '1') p->sv.rec_spec |= 2;
     p->sv.rec_code = 2;
   }
 
@@ -908,7 +978,9 @@ int epb_recv_slab_ex(epb_pool* p, void** slab, int* row0, int* n_rows) {
   if (have < want) return fail(EPB_ERR_STATE, "recv: fewer than batch_size envs outstanding");
   void* dst = nullptr;
   lk.unlock();
-  int rc = get_slab(p, &dst);
+  bool dst_ids_ok = false;
+  int rc = get_slab(p, &dst, &dst_ids_ok);
+  if (rc == EPB_OK && dst_ids_ok) set_ids_ok(p, dst, false);
   lk.lock();
   if (rc != EPB_OK) return rc;
   int filled = 0;
@@ -1047,12 +1119,16 @@ int run_chain(epb_pool* p, cudaStream_t st, const ChainKey& c, bool fork, cudaEv
               cudaEvent_t ev1) {
   const size_t row = (size_t)p->act.row_bytes * p->N;
   const char* base = static_cast<const char*>(c.actions);
-  const bool rec = fork && p->refill_fn;
+  const bool rec = fork && p->refill_fn && !(p->sv.rec_spec & 2);
   const bool xfork = fork && c.exchange;
   const int D = p->x_depth;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
   auto mark = [&](cudaEvent_t ev) -> int {
-    if (!fork) {
-      EPB_CUDA(cudaEventRecord(ev, st));
+    if (!fork) {  // in series; inside a capture the timed events are external event nodes
+      if (capturing) EPB_CUDA(cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal));
+      else EPB_CUDA(cudaEventRecord(ev, st));
       return EPB_OK;
     }
     EPB_CUDA(cudaEventRecord(p->ev_mark, st));
@@ -1452,6 +1528,49 @@ int epb_state_import(epb_pool* p, const void* host_src) {
     if (rc != EPB_OK) return rc;
     EPB_CUDA(cudaStreamSynchronize(p->stream));
   }
+  return EPB_OK;
+}
+
+namespace {
+// 8 independent DFMA chains per thread: the fp64 FMA pipe's sustained rate (the denominator of
+// HalfCheetah's compute roofline; the profiling guide has no fp64 figure for B200).
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4,
+         a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (r == 12345.678) out[0] = r;  // never true: keeps the chains alive
+}
+}  // namespace
+
+int epb_fp64_peak_gflops(int device, double* gflops_out) {
+  if (!gflops_out) return fail(EPB_ERR_INVALID, "null argument");
+  DeviceGuard guard(device);
+  EPB_CUDA(guard.status);
+  double* d = nullptr;
+  EPB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d), 8));
+  cudaEvent_t e0, e1;
+  EPB_CUDA(cudaEventCreate(&e0));
+  EPB_CUDA(cudaEventCreate(&e1));
+  const int grid = 148 * 8, iters = 1 << 14;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    EPB_CUDA(cudaEventRecord(e0, 0));
+    fp64_peak_kernel<<<grid, 256>>>(d, iters, 1.0 + rep);
+    EPB_CUDA(cudaEventRecord(e1, 0));
+    EPB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    EPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *gflops_out = 2.0 * 8.0 * iters * 256.0 * grid / (best * 1e-3) / 1e9;
   return EPB_OK;
 }
 

@@ -43,8 +43,9 @@ struct StateView {
   void* rec;              // [N][NR] real, row per env (one or two 16-byte loads per lane)
   uint8_t* rstat;         // [N] 1 = record full; rec_code = consumed, refill pending
   int32_t rec_code;       // value a consuming step writes into rstat (2 | 3, step parity)
-  int32_t rec_spec;       // 1 = load the record with the state (L2-resident batch sizes),
-                          // 0 = only on the lanes that reset
+  int32_t rec_spec;       // bit 0: load the record with the state (speculatively, every lane)
+                          // instead of only on the lanes that reset; bit 1: timing
+                          // experiments only -- no refill launches, no full-record check
 };
 
 // Output columns for one batch (pointers into a packed slab or caller arrays).
@@ -372,16 +373,18 @@ __device__ __forceinline__ void env_step(const StateView& sv, int eid, int& flag
     // free; a done env's stale state is finite, the result is discarded) and the resetting
     // lanes then take their record.  With a branch, ptxas sinks the state loads into the
     // step side -- behind the arrival of `flags`, one more dependent L2 round trip.
+    if (reset && rstat < 0) {
+      // the record was not loaded with the state (large batches, rec_spec = 0): fetch it on
+      // the resetting lanes NOW, ahead of the step arithmetic that hides its latency
+      rstat = sv.rstat[eid];
+      Env::load_rec(sv, eid, rec);
+    }
     typename Env::State s1 = s;
     StepOut so1 = so;
     int cur1 = cur + 1, done1 = 0;
     Env::step(sv, s1, a, cur1, done1, nullptr, so1);
     if (reset) {
-      if (rstat < 0) {  // not loaded with the state: fetch it now (large batches)
-        rstat = sv.rstat[eid];
-        Env::load_rec(sv, eid, rec);
-      }
-      if (rstat != 1) __trap();
+      if (rstat != 1 && !(sv.rec_spec & 2)) __trap();
       rstat = sv.rec_code;
       sv.rstat[eid] = (uint8_t)rstat;
     }
@@ -450,7 +453,7 @@ step_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ acti
     int mt_idx = 0, rstat = -1;
     typename Env::State rec;
     if constexpr (kRec) {
-      if (sv.rec_spec) {  // the record rides with the state loads: no dependent round trip
+      if (sv.rec_spec & 1) {  // the record rides with the state loads: no dependent round trip
         rstat = sv.rstat[eid];
         Env::load_rec(sv, eid, rec);
       }

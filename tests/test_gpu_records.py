@@ -115,12 +115,14 @@ def test_rollout_then_steps_share_the_record_stream(capi, task):
             assert_batch_equal(pool.step(a), orc.step(a), task, 1e-6, f"step after rollout {t}")
 
 
-def test_large_batch_uses_the_conditional_record_load(capi):
-    """Above the L2-resident size the record is fetched only by resetting lanes
-    (StateView::rec_spec = 0); same trajectories."""
+@pytest.mark.parametrize("spec", ["0", "1"])
+def test_both_record_load_variants(capi, monkeypatch, spec):
+    """The record is fetched only by the resetting lanes (default) or speculatively with the
+    state by every lane (ENVPOOL_B200_REC_SPEC=1, read at pool creation); same trajectories."""
     import torch
     from oracle.oracle_lib import OraclePool
 
+    monkeypatch.setenv("ENVPOOL_B200_REC_SPEC", spec)
     N, P = 300000, 4096
     pool = capi.CPool("CartPole", N, seed=1, max_episode_steps=6)
     orc = OraclePool("CartPole", P, seed=1, max_episode_steps=6)
