@@ -279,11 +279,11 @@ def measure_exchange(torch, dist, timer, pool, world, rank, dev, K, lead):
             "nvlink_gbs_in_per_gpu": wire * K / (ms * 1e-3) / 1e9,
             "wire_bytes_per_env_step": wire_bytes_per_env(pool),
             "ring_depth": pool.exchange_depth,
-            "api": "epb_step_exchange_many_device: per step one credit kernel, the step kernel "
-                   "(writes its slice, forwards env keys + reward + packed word to every peer "
-                   "over NVLink, publishes) and one wait kernel (acquires every peer's flag, "
-                   "re-expands the common columns); CUDA-graph replay, waits on a parallel "
-                   "branch"}
+            "api": "epb_step_exchange_many_device: per step the step kernel (writes its slice, "
+                   "checks the ring credit, forwards env keys + reward + packed word to every "
+                   "peer over NVLink, publishes) and one wait kernel (acquires every peer's "
+                   "flag, re-expands the common columns); CUDA-graph replay, waits and record "
+                   "refills on parallel branches"}
 
 
 def run_allgather(args, torch, dist, pool, actions, dev, world):

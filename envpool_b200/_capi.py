@@ -456,10 +456,10 @@ class CPool:
         return self.lib.epb_bytes_per_env_step(self.h)
 
     def state_layout(self) -> Dict[str, int]:
-        out = (ctypes.c_int64 * 10)()
+        out = (ctypes.c_int64 * 12)()
         _check(self.lib.epb_state_layout(self.h, out))
         names = ["flags", "mt_idx", "istate", "rstate", "mt", "NI", "NR", "real_size",
-                 "rec", "rstat"]
+                 "rec", "rcons", "rprod", "rec_q"]
         return dict(zip(names, [int(v) for v in out]))
 
     def state_arrays(self, blob: np.ndarray) -> Dict[str, np.ndarray]:
@@ -478,10 +478,13 @@ class CPool:
             out["rstate"] = blob[lay["rstate"]:lay["rstate"] + nb].view(real).reshape(
                 lay["NR"], n)
         if lay["rec"] >= 0:
-            # reset-ahead records: rec[e] = the env's NEXT initial state, rstat[e] == 1 = full
-            nb = lay["real_size"] * n * lay["NR"]
-            out["rec"] = blob[lay["rec"]:lay["rec"] + nb].view(real).reshape(n, lay["NR"])
-            out["rstat"] = blob[lay["rstat"]:lay["rstat"] + n]
+            # reset-ahead record rings: rec[e, i % Q] = the env's i-th initial state,
+            # records rcons[e] .. rprod[e] - 1 (uint8 counters, mod 256) are valid
+            q = lay["rec_q"]
+            nb = lay["real_size"] * n * lay["NR"] * q
+            out["rec"] = blob[lay["rec"]:lay["rec"] + nb].view(real).reshape(n, q, lay["NR"])
+            out["rcons"] = blob[lay["rcons"]:lay["rcons"] + n]
+            out["rprod"] = blob[lay["rprod"]:lay["rprod"] + n]
         return out
 
     def state_export(self) -> np.ndarray:

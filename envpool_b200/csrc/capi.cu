@@ -141,8 +141,9 @@ struct epb_pool {
   // (its parity is the consume code) and the side stream + events that put refill(t) on a
   // parallel branch of the engine's captured step chains
   launch_fn refill_fn = nullptr;
-  uint64_t seq = 0;
-  int last_code = 0;  // consume code of the most recent step launch
+  uint64_t seq = 0;        // step launches so far
+  int refill_every = 8;    // a refill launch after every this many step launches (< rec_q)
+  int since_refill = 0;    // step launches since the last refill
   cudaStream_t side = nullptr;
   cudaEvent_t ev_step[2] = {nullptr, nullptr}, ev_refill[2] = {nullptr, nullptr};
   MjcPool* mjc = nullptr;
@@ -341,6 +342,8 @@ push_kernel(const PeerView* __restrict__ pv, int n) {
   const int world = pv->world, rank = pv->rank;
   const char* __restrict__ src = pv->slice[rank];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  peer_credit(pv);
+  __syncthreads();
   for (int k = 0; k < pv->ncols; ++k) {
     const int64_t off = pv->col_off[k];
     const int64_t n16 = ((int64_t)n * pv->col_rb[k] + 15) >> 4;
@@ -352,29 +355,6 @@ push_kernel(const PeerView* __restrict__ pv, int n) {
     }
   }
   peer_publish(pv);
-}
-
-// One warp in front of step t (t = ctl->seq, the steps this rank has pushed so far): lane g
-// waits until rank g has released step t - D, i.e. ack_flag[g] >= t - D + 1, so that slot
-// t % D may be overwritten everywhere.  Bounded like the data wait.
-__global__ void credit_kernel(const unsigned long long* ack, int world, int depth,
-                              ExchangeCtl* ctl, long long timeout_ns) {
-  const unsigned long long t = ctl->seq;
-  if (t < (unsigned long long)depth) return;
-  const unsigned long long need = t - depth + 1;
-  if ((int)threadIdx.x < world) {
-    long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (ld_acquire_sys(ack + threadIdx.x) < need) {
-      long long t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > timeout_ns) {
-        atomicExch(&ctl->error, 1);
-        break;
-      }
-      __nanosleep(64);
-    }
-  }
 }
 
 struct WaitArgs {
@@ -481,6 +461,9 @@ int upload_views(epb_pool* p) {
     pv.world = p->x_world;
     pv.rank = p->x_rank;
     pv.ctl = p->x_ctl();
+    pv.ack = reinterpret_cast<const unsigned long long*>(p->x_base + p->x_ack_off);
+    pv.timeout_ns = p->x_timeout_ns;
+    pv.depth = p->x_depth;
     for (int g = 0; g < p->x_world; ++g) {
       pv.slice[g] = p->x_peer[g] + p->x_mine(slot);
       pv.flag[g] =
@@ -510,22 +493,23 @@ int upload_views(epb_pool* p) {
   return EPB_OK;
 }
 
-// Refill every record consumed with `code` (0 = all that are not full) on `stream`.
-int launch_refill(epb_pool* p, int code, cudaStream_t stream) {
+// Refill every env's record ring to full on `stream`.
+int launch_refill(epb_pool* p, cudaStream_t stream) {
   LaunchArgs a{};
   a.sv = p->sv;
   a.stream = stream;
-  a.refill_code = code;
   EPB_CUDA(p->refill_fn(a));
   ++p->launches;
+  p->since_refill = 0;
   return EPB_OK;
 }
 
 // Launch one batch step on `stream`.  d_action/d_ids are device pointers.
-// Record envs: the step is followed by the refill of the records it consumed -- on the same
-// stream (chain_k < 0: direct launches and user-driven captures), or, for step k of an
-// engine-captured chain (chain_k >= 0), on the pool's side stream so that refill(k) runs
-// beside step k+1; step k+2 waits for it (the caller enqueues that wait and the final join).
+// Record envs (refill policy): chain_k == -1 (direct launches, user-driven captures): a refill
+// on the same stream after every `refill_every`-th step launch -- an env consumes at most one
+// record per launch, the ring holds rec_q > refill_every.  chain_k == -2: the caller places the
+// refill itself (host path: behind the D2H copy; engine-captured chains: on a parallel graph
+// branch every refill_every steps, run_chain).
 int launch_batch(epb_pool* p, const void* d_action, const int32_t* d_ids, int n,
                  int force_reset, char* d_slab, cudaStream_t stream,
                  const PeerView* peers = nullptr, int chain_k = -1, int32_t* wire = nullptr,
@@ -542,8 +526,6 @@ int launch_batch(epb_pool* p, const void* d_action, const int32_t* d_ids, int n,
   }
   LaunchArgs a{};
   a.sv = p->sv;
-  const int code = 2 + (int)(p->seq & 1);
-  a.sv.rec_code = code;
   a.ov = p->slab_view(d_slab);
   a.ov.wire = wire;
   a.action = d_action;
@@ -556,15 +538,9 @@ int launch_batch(epb_pool* p, const void* d_action, const int32_t* d_ids, int n,
   EPB_CUDA(p->step_fn(a));
   ++p->launches;
   ++p->seq;
-  p->last_code = code;
-  if (p->refill_fn && chain_k != -2 && !(p->sv.rec_spec & 2)) {
-    if (chain_k < 0) return launch_refill(p, code, stream);
-    const int h = chain_k & 1;
-    EPB_CUDA(cudaEventRecord(p->ev_step[h], stream));
-    EPB_CUDA(cudaStreamWaitEvent(p->side, p->ev_step[h], 0));
-    int rc = launch_refill(p, code, p->side);
-    if (rc != EPB_OK) return rc;
-    EPB_CUDA(cudaEventRecord(p->ev_refill[h], p->side));
+  if (p->refill_fn) {
+    ++p->since_refill;
+    if (chain_k == -1 && p->since_refill >= p->refill_every) return launch_refill(p, stream);
   }
   return EPB_OK;
 }
@@ -649,7 +625,7 @@ int host_submit(epb_pool* p, const void* action, const int32_t* env_ids, int n,
     p->pending.push_back(Pending{slab, n, 0, ev, false});
     p->leases.emplace_back(slab, 1);  // the queue's own reference
   }
-  if (p->refill_fn && !(p->sv.rec_spec & 2)) return launch_refill(p, p->last_code, p->stream);
+  if (p->refill_fn && p->since_refill >= p->refill_every) return launch_refill(p, p->stream);
   return EPB_OK;
 }
 
@@ -716,9 +692,20 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
   int64_t o_rst = o_ist + al(4 * N * (p->NI > 0 ? p->NI : 1));
   int64_t o_mt = o_rst + al((int64_t)p->real_size * N * (p->NR > 0 ? p->NR : 1));
   const bool has_rec = kind <= EPB_MOUNTAIN_CAR_CONTINUOUS;  // classic_control: record resets
+  int rec_q = 16;  // records per env; ENVPOOL_B200_REC_Q = 4 | 8 | 16
+  if (const char* rq = getenv("ENVPOOL_B200_REC_Q")) {
+    int v = atoi(rq);
+    if (v == 4 || v == 8 || v == 16) rec_q = v;
+  }
+  p->refill_every = rec_q / 2;  // <= rec_q - 2: see run_chain for the bound
+  if (const char* re = getenv("ENVPOOL_B200_REFILL_EVERY")) {
+    int v = atoi(re);
+    if (v >= 1 && v <= rec_q - 2) p->refill_every = v;
+  }
   int64_t o_rec = o_mt + al(4 * N * kMtN);
-  int64_t o_rstat = o_rec + (has_rec ? al((int64_t)p->real_size * N * p->NR) : 0);
-  p->state_bytes = o_rstat + (has_rec ? al(N) : 0);
+  int64_t o_rcons = o_rec + (has_rec ? al((int64_t)p->real_size * N * p->NR * rec_q) : 0);
+  int64_t o_rprod = o_rcons + (has_rec ? al(N) : 0);
+  p->state_bytes = o_rprod + (has_rec ? al(N) : 0);
   cudaError_t e = cudaMalloc(&p->d_state_blob, (size_t)p->state_bytes);
   if (e == cudaSuccess) e = cudaMemset(p->d_state_blob, 0, (size_t)p->state_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&p->d_slab, (size_t)p->slab_bytes);
@@ -783,17 +770,9 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
   p->sv.mt = reinterpret_cast<uint32_t*>(blob + o_mt);
   if (has_rec) {
     p->sv.rec = blob + o_rec;
-    p->sv.rstat = reinterpret_cast<uint8_t*>(blob + o_rstat);
-    // Load the record with the state while state + records + slab stay L2-resident; for
-    // larger batches only the resetting lanes fetch it.  ENVPOOL_B200_REC_SPEC=0|1 overrides.
-    // Measured (profiles/r2_step_ab.md): with the conditional load issued ahead of the step
-    // arithmetic the two variants are within noise at 65536 envs and the conditional one wins
-    // above L2 size, so it is the default; ENVPOOL_B200_REC_SPEC=1 selects the speculative load.
-    p->sv.rec_spec = 0;
-    if (const char* rs = getenv("ENVPOOL_B200_REC_SPEC")) p->sv.rec_spec = rs[0] == '1';
-    if (const char* nr = getenv("ENVPOOL_B200_NO_REFILL"))  // timing experiment, wrong results
-      if (nr[0] == '1') p->sv.rec_spec |= 2;
-    p->sv.rec_code = 2;
+    p->sv.rcons = reinterpret_cast<uint8_t*>(blob + o_rcons);
+    p->sv.rprod = reinterpret_cast<uint8_t*>(blob + o_rprod);
+    p->sv.rec_q = rec_q;
   }
 
   if (kind <= EPB_MOUNTAIN_CAR_CONTINUOUS) {
@@ -817,11 +796,10 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
     e = cudaGetLastError();
     ++p->launches;
   }
-  if (e == cudaSuccess && p->refill_fn) {  // first records (rstat was zeroed: none is full)
+  if (e == cudaSuccess && p->refill_fn) {  // the first rec_q records of every env
     LaunchArgs ra{};
     ra.sv = p->sv;
     ra.stream = p->stream;
-    ra.refill_code = 0;
     e = p->refill_fn(ra);
     ++p->launches;
   }
@@ -1098,6 +1076,7 @@ int epb_rollout_device(epb_pool* p, const void* d_actions, int T, void* const* d
   a.stream = s;
   EPB_CUDA(p->rollout_fn(a));
   ++p->launches;
+  p->since_refill = 0;  // the rollout kernel leaves every record ring full
   return EPB_OK;
 }
 
@@ -1109,7 +1088,12 @@ int exchange_wait_launch(epb_pool* p, cudaStream_t s);
 
 // K consecutive sync steps on `st`, step k reading action row (t0 + k) % T.  `fork` (only
 // while capturing) puts the off-critical-path kernels on parallel graph branches:
-//   * refill(k) (record envs) on p->side: beside step k+1, awaited by step k+2;
+//   * record envs: one refill on p->side after every refill_every-th step (and after the
+//     last), beside the following steps.  Refill j (after step k_j) is awaited by the first
+//     step after refill j+1 is launched, i.e. it has refill_every steps to finish.  Between
+//     the snapshot refill j works from and the completion of refill j+1 lie at most
+//     2 * refill_every steps = at most refill_every consumptions per env (a step that resets
+//     is never `done`), so a ring of rec_q >= refill_every + 2 records never runs dry;
 //   * exchange chains: wait_derive(k) on p->x_side: step k+1 .. k+D-2 compute and push while
 //     the batch of step k is still arriving; step k+D-1 waits for it (its credit needs the
 //     local release as well as the peers');
@@ -1119,8 +1103,11 @@ int run_chain(epb_pool* p, cudaStream_t st, const ChainKey& c, bool fork, cudaEv
               cudaEvent_t ev1) {
   const size_t row = (size_t)p->act.row_bytes * p->N;
   const char* base = static_cast<const char*>(c.actions);
-  const bool rec = fork && p->refill_fn && !(p->sv.rec_spec & 2);
+  const bool rec = fork && p->refill_fn;
   const bool xfork = fork && c.exchange;
+  const int R = p->refill_every;
+  int nref = 0;          // refills launched so far in this chain
+  bool after_trigger = false;
   const int D = p->x_depth;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cap);
@@ -1145,12 +1132,14 @@ int run_chain(epb_pool* p, cudaStream_t st, const ChainKey& c, bool fork, cudaEv
       if (rc != EPB_OK) return rc;
       marked = true;
     }
-    if (rec && k >= 2) EPB_CUDA(cudaStreamWaitEvent(st, p->ev_refill[k & 1], 0));
+    if (rec && after_trigger && nref >= 2)  // the refill before the one just launched
+      EPB_CUDA(cudaStreamWaitEvent(st, p->ev_refill[(nref - 2) & 1], 0));
+    after_trigger = false;
     int rc;
     if (c.exchange) {
       if (xfork && k >= D - 1)
         EPB_CUDA(cudaStreamWaitEvent(st, p->x_ev_wait[(k - (D - 1)) % D], 0));
-      rc = exchange_step(p, a, st, rec ? k : -1, nx);
+      rc = exchange_step(p, a, st, rec ? -2 : -1, nx);
       if (rc != EPB_OK) return rc;
       if (xfork) {
         EPB_CUDA(cudaEventRecord(p->x_ev_step[k % D], st));
@@ -1163,9 +1152,19 @@ int run_chain(epb_pool* p, cudaStream_t st, const ChainKey& c, bool fork, cudaEv
         if (rc != EPB_OK) return rc;
       }
     } else {
-      rc = launch_batch(p, a, nullptr, p->N, 0, p->d_slab, st, nullptr, rec ? k : -1, nullptr,
+      rc = launch_batch(p, a, nullptr, p->N, 0, p->d_slab, st, nullptr, rec ? -2 : -1, nullptr,
                         nx);
       if (rc != EPB_OK) return rc;
+    }
+    if (rec && ((k % R) == R - 1 || k == c.K - 1)) {
+      const int h = nref & 1;
+      EPB_CUDA(cudaEventRecord(p->ev_step[h], st));
+      EPB_CUDA(cudaStreamWaitEvent(p->side, p->ev_step[h], 0));
+      rc = launch_refill(p, p->side);
+      if (rc != EPB_OK) return rc;
+      EPB_CUDA(cudaEventRecord(p->ev_refill[h], p->side));
+      ++nref;
+      after_trigger = true;
     }
     if (ev1 && k + 1 == c.mark1) {
       if (xfork) {  // an exchanged step is complete when its batch has arrived
@@ -1178,10 +1177,8 @@ int run_chain(epb_pool* p, cudaStream_t st, const ChainKey& c, bool fork, cudaEv
     }
   }
   // join every branch
-  if (rec) {
-    EPB_CUDA(cudaStreamWaitEvent(st, p->ev_refill[(c.K - 1) & 1], 0));
-    if (c.K >= 2) EPB_CUDA(cudaStreamWaitEvent(st, p->ev_refill[(c.K - 2) & 1], 0));
-  }
+  if (rec && nref > 0)  // refills are serialised on p->side: the last one implies the rest
+    EPB_CUDA(cudaStreamWaitEvent(st, p->ev_refill[(nref - 1) & 1], 0));
   if (xfork) EPB_CUDA(cudaStreamWaitEvent(st, p->x_ev_wait[(c.K - 1) % D], 0));
   if (fork && (marked || (ev1 && c.mark1 > 0))) {
     EPB_CUDA(cudaEventRecord(p->ev_mark, p->mark_side));
@@ -1205,6 +1202,10 @@ int chain_entry(epb_pool* p, const void* d_actions, int T_stream, int t0, int K,
   DeviceGuard guard(p->cfg.device);
   EPB_CUDA(guard.status);
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
+  if (p->refill_fn && p->since_refill > 0) {  // chains start from full record rings
+    int rc = launch_refill(p, s);
+    if (rc != EPB_OK) return rc;
+  }
   ChainKey key{d_actions, T_stream, t0, K, timed ? mark0 : -1, timed ? mark1 : -1, exchange,
                exchange ? (int)(p->x_steps % p->x_depth) : 0, s};
   cudaEvent_t ev0 = timed ? p->ev_t0 : nullptr, ev1 = timed ? p->ev_t1 : nullptr;
@@ -1234,6 +1235,7 @@ int chain_entry(epb_pool* p, const void* d_actions, int T_stream, int t0, int K,
       p->x_steps = xs;
       p->x_waited = xw;
       p->seq = sq;
+      p->since_refill = 0;
       cudaError_t e = cudaStreamEndCapture(s, &g);
       if (rc != EPB_OK) {
         if (g) cudaGraphDestroy(g);
@@ -1371,8 +1373,8 @@ int epb_exchange_attach_ipc(epb_pool* p, const void* ipc_handles) {
 
 namespace {
 
-// One exchanged step on `s`: credit (slot t % D is free everywhere), the step kernel writing
-// slot[t % D][rank] of the local allocation and forwarding its wire columns, publication.
+// One exchanged step on `s`: the step kernel writes slot[t % D][rank] of the local allocation,
+// checks the credit (slot t % D released everywhere), forwards its wire columns, publishes.
 int exchange_step(epb_pool* p, const void* d_action, cudaStream_t s, int chain_k,
                   const void* next_action) {
   const int D = p->x_depth;
@@ -1384,13 +1386,6 @@ int exchange_step(epb_pool* p, const void* d_action, cudaStream_t s, int chain_k
                 "exchange: too many exchanged steps without epb_exchange_wait (at most "
                 "depth - 1 may be outstanding)");
   const int slot = (int)(t % D);
-  if (t >= (uint64_t)D || p->x_world > 0) {
-    credit_kernel<<<1, 32, 0, s>>>(
-        reinterpret_cast<const unsigned long long*>(p->x_base + p->x_ack_off), p->x_world, D,
-        p->x_ctl(), p->x_timeout_ns);
-    EPB_CUDA(cudaGetLastError());
-    ++p->launches;
-  }
   char* mine = p->x_base + p->x_mine(slot);
   int32_t* wire = reinterpret_cast<int32_t*>(mine + p->slab_bytes);
   const int force = d_action ? 0 : 1;
@@ -1504,7 +1499,9 @@ int epb_state_layout(const epb_pool* p, int64_t* out) {
   out[6] = p->NR;
   out[7] = p->real_size;
   out[8] = p->sv.rec ? static_cast<const char*>(p->sv.rec) - blob : -1;
-  out[9] = p->sv.rstat ? reinterpret_cast<const char*>(p->sv.rstat) - blob : -1;
+  out[9] = p->sv.rcons ? reinterpret_cast<const char*>(p->sv.rcons) - blob : -1;
+  out[10] = p->sv.rprod ? reinterpret_cast<const char*>(p->sv.rprod) - blob : -1;
+  out[11] = p->sv.rec_q;
   return EPB_OK;
 }
 int epb_state_export(epb_pool* p, void* host_dst) {
@@ -1522,9 +1519,9 @@ int epb_state_import(epb_pool* p, const void* host_src) {
   EPB_CUDA(cudaStreamSynchronize(p->stream));
   EPB_CUDA(cudaMemcpy(p->d_state_blob, host_src, (size_t)p->state_bytes, cudaMemcpyHostToDevice));
   if (p->refill_fn) {
-    // a blob may carry records marked not-full (a hand-edited RNG table wants its next reset
-    // drawn from that table): draw them now, so every record is full before the next step
-    int rc = launch_refill(p, 0, p->stream);
+    // a blob may carry a ring that is not full (a hand-edited RNG table wants its next resets
+    // drawn from that table: rprod = rcons empties the ring): fill it now
+    int rc = launch_refill(p, p->stream);
     if (rc != EPB_OK) return rc;
     EPB_CUDA(cudaStreamSynchronize(p->stream));
   }

@@ -87,13 +87,14 @@ __device__ __forceinline__ void store_real(const StateView& sv, int eid,
   for (int k = 0; k < NR; ++k) p[(int64_t)k * sv.n_envs] = s.v[k];
 }
 
-// Reset-ahead record of a RealState env: rec[e] = NR reals, contiguous (8 / 16 / 32 bytes).
+// Reset-ahead record of a RealState env: rec[e][slot] = NR reals, contiguous (8 / 16 / 32 B).
 template <typename R, int NR>
-__device__ __forceinline__ void load_rec_real(const StateView& sv, int eid,
+__device__ __forceinline__ void load_rec_real(const StateView& sv, int eid, int slot,
                                               RealState<R, NR>& s) {
   constexpr int kBytes = NR * (int)sizeof(R);
   static_assert(kBytes == 8 || kBytes % 16 == 0, "record must be 8 bytes or 16-byte units");
-  const char* p = static_cast<const char*>(sv.rec) + (int64_t)eid * kBytes;
+  const char* p = static_cast<const char*>(sv.rec) +
+                  ((int64_t)eid * sv.rec_q + slot) * kBytes;
   if constexpr (kBytes == 8) {
     uint2 q = *reinterpret_cast<const uint2*>(p);
     memcpy(&s.v[0], &q, 8);
@@ -106,10 +107,10 @@ __device__ __forceinline__ void load_rec_real(const StateView& sv, int eid,
   }
 }
 template <typename R, int NR>
-__device__ __forceinline__ void store_rec_real(const StateView& sv, int eid,
+__device__ __forceinline__ void store_rec_real(const StateView& sv, int eid, int slot,
                                                const RealState<R, NR>& s) {
   constexpr int kBytes = NR * (int)sizeof(R);
-  char* p = static_cast<char*>(sv.rec) + (int64_t)eid * kBytes;
+  char* p = static_cast<char*>(sv.rec) + ((int64_t)eid * sv.rec_q + slot) * kBytes;
   if constexpr (kBytes == 8) {
     uint2 q;
     memcpy(&q, &s.v[0], 8);
@@ -125,12 +126,13 @@ __device__ __forceinline__ void store_rec_real(const StateView& sv, int eid,
 }
 #define EPB_REC_RESET_MEMBERS                                                               \
   static constexpr bool kRecReset = true;                                                   \
-  static __device__ __forceinline__ void load_rec(const StateView& sv, int e, State& s) {   \
-    load_rec_real(sv, e, s);                                                                \
+  static __device__ __forceinline__ void load_rec(const StateView& sv, int e, int slot,     \
+                                                  State& s) {                               \
+    load_rec_real(sv, e, slot, s);                                                          \
   }                                                                                         \
-  static __device__ __forceinline__ void store_rec(const StateView& sv, int e,              \
+  static __device__ __forceinline__ void store_rec(const StateView& sv, int e, int slot,    \
                                                    const State& s) {                        \
-    store_rec_real(sv, e, s);                                                               \
+    store_rec_real(sv, e, slot, s);                                                         \
   }
 
 // ----------------------------------------------------------------------------- CartPole

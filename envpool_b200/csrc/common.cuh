@@ -36,16 +36,16 @@ struct StateView {
   void* rstate;           // [NR][N] real state (double or float)
   int32_t* istate;        // [NI][N] integer state
   // Reset-ahead records (envs whose Reset() is a pure function of their RNG stream:
-  // classic_control).  rec[e] always holds the env's NEXT initial state, drawn ahead of time
-  // by refill_kernel, so the step kernel's auto-reset is a load instead of a dependent
-  // mt19937 round trip on one lane of the warp.  The per-env draw ORDER is unchanged (these
-  // envs draw only at reset), so trajectories stay those of std::mt19937(seed + env_id).
-  void* rec;              // [N][NR] real, row per env (one or two 16-byte loads per lane)
-  uint8_t* rstat;         // [N] 1 = record full; rec_code = consumed, refill pending
-  int32_t rec_code;       // value a consuming step writes into rstat (2 | 3, step parity)
-  int32_t rec_spec;       // bit 0: load the record with the state (speculatively, every lane)
-                          // instead of only on the lanes that reset; bit 1: timing
-                          // experiments only -- no refill launches, no full-record check
+  // classic_control).  Every env owns a ring of rec_q records = its NEXT rec_q initial states,
+  // drawn ahead of time by refill_kernel, so the step kernel's auto-reset is a 32-byte load
+  // instead of a dependent mt19937 round trip on one lane of the warp.  Records are produced
+  // and consumed in order and these envs draw only at reset, so every trajectory stays the one
+  // std::mt19937(seed + env_id) gives.  rcons / rprod count consumed / produced records
+  // (mod 256; valid = rprod - rcons <= rec_q); slot of record i is i % rec_q.
+  void* rec;              // [N][rec_q][NR] real: one or two 16-byte loads per record
+  uint8_t* rcons;         // [N] records consumed so far (written by the step kernels)
+  uint8_t* rprod;         // [N] records produced so far (written by refill_kernel)
+  int32_t rec_q;          // ring size, a power of two <= 16
 };
 
 // Output columns for one batch (pointers into a packed slab or caller arrays).
@@ -353,17 +353,16 @@ struct UsesRec<Env, typename std::enable_if<Env::kRecReset>::type> {
 
 // One EnvStep (env.h:184-222) incl. the auto-reset decision (async_envpool.h:127).
 //
-// Reset, record envs: the state becomes the record (`rec`, already loaded when
-// sv.rec_spec), the record is marked consumed and refill_kernel draws the next one off the
-// critical path.  A record that is not full when it is needed is an engine invariant
-// violation (every consuming launch is followed by a refill before the same env can reset
-// again): trap, never step on with stale randomness.
+// Reset, record envs: the state becomes the env's next record (slot rcons % rec_q) and the
+// consume counter moves on; refill_kernel redraws consumed slots off the critical path.  The
+// ring can never run dry: a step that resets is never `done`, so an env consumes at most one
+// record every two steps, and the engine refills at least every rec_q - 2 launches (capi.cu).
 // Reset, other envs: the draws happen here (Mt, chunked table).
 template <class Env>
 __device__ __forceinline__ void env_step(const StateView& sv, int eid, int& flags,
                                          typename Env::State& s, typename Env::Act a,
                                          bool force_reset, StepOut& so, int& mt_idx,
-                                         typename Env::State& rec, int& rstat) {
+                                         int rcons) {
   int done = flags & 1;
   int cur = flags >> 1;
   const bool reset = force_reset || done;
@@ -373,21 +372,16 @@ __device__ __forceinline__ void env_step(const StateView& sv, int eid, int& flag
     // free; a done env's stale state is finite, the result is discarded) and the resetting
     // lanes then take their record.  With a branch, ptxas sinks the state loads into the
     // step side -- behind the arrival of `flags`, one more dependent L2 round trip.
-    if (reset && rstat < 0) {
-      // the record was not loaded with the state (large batches, rec_spec = 0): fetch it on
-      // the resetting lanes NOW, ahead of the step arithmetic that hides its latency
-      rstat = sv.rstat[eid];
-      Env::load_rec(sv, eid, rec);
+    typename Env::State rec;
+    if (reset) {
+      // issued NOW, ahead of the step arithmetic that hides its latency
+      Env::load_rec(sv, eid, rcons & (sv.rec_q - 1), rec);
+      sv.rcons[eid] = (uint8_t)(rcons + 1);
     }
     typename Env::State s1 = s;
     StepOut so1 = so;
     int cur1 = cur + 1, done1 = 0;
     Env::step(sv, s1, a, cur1, done1, nullptr, so1);
-    if (reset) {
-      if (rstat != 1 && !(sv.rec_spec & 2)) __trap();
-      rstat = sv.rec_code;
-      sv.rstat[eid] = (uint8_t)rstat;
-    }
     s = reset ? rec : s1;
     so.reward = reset ? 0.0f : so1.reward;
     so.extra = reset ? 0.0f : so1.extra;
@@ -450,13 +444,9 @@ step_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ acti
     eid = env_ids ? env_ids[row] : row;
     if (!force_reset) a = action[row];
     flags = sv.flags[eid];
-    int mt_idx = 0, rstat = -1;
-    typename Env::State rec;
+    int mt_idx = 0, rcons = 0;
     if constexpr (kRec) {
-      if (sv.rec_spec & 1) {  // the record rides with the state loads: no dependent round trip
-        rstat = sv.rstat[eid];
-        Env::load_rec(sv, eid, rec);
-      }
+      rcons = sv.rcons[eid];  // rides with the state loads: the record's slot is known at once
     } else if (kRng) {
       mt_idx = sv.mt_idx[eid];
     }
@@ -469,7 +459,7 @@ step_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ acti
     if (next_action && (threadIdx.x & 31) == 0)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(next_action + row));
     pin_value(a);
-    env_step<Env>(sv, eid, flags, s, a, force_reset != 0, so, mt_idx, rec, rstat);
+    env_step<Env>(sv, eid, flags, s, a, force_reset != 0, so, mt_idx, rcons);
     Env::store(sv, eid, s);
     sv.flags[eid] = flags;
     if (!kRec && kRng && mt_idx != mt_idx0) sv.mt_idx[eid] = mt_idx;
@@ -485,30 +475,38 @@ step_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ acti
   if (peers) peer_forward_rows<kB>(peers, (int64_t)blockIdx.x * kB, n);
 }
 
-// Draws the next initial state of every env whose record was consumed by the step with
-// `code` (0: every record that is not full -- pool creation, state import).  Runs BEHIND the
-// step that consumed and, in the engine's captured step chains, beside the next step (a
-// parallel graph branch): an env that resets at step t cannot reset again before t+2, which
-// waits for this kernel.  The only kernel that touches the mt19937 tables of record envs.
+// Refills every env's record ring to rec_q valid records (draws rec_q - (rprod - rcons) new
+// initial states, in order).  Runs BEHIND the steps that consumed and, in the engine's captured
+// step chains, beside the following steps (a parallel graph branch).  The only kernel that
+// touches the mt19937 tables of record envs.  Reading a stale rcons (a concurrent step has
+// just consumed) only makes it refill one record fewer; the slots it writes are never the
+// ones a concurrent step reads (those lie in [rcons, rprod), these in [rprod, rcons + rec_q)).
 template <class Env>
-__global__ void __launch_bounds__(kBlock) refill_kernel(StateView sv, int code) {
+__global__ void __launch_bounds__(kBlock) refill_kernel(StateView sv) {
   const int e = blockIdx.x * kBlock + threadIdx.x;
   if (e >= sv.n_envs) return;
-  const int st = sv.rstat[e];
-  if (code ? st != code : st == 1) return;
+  const int q = sv.rec_q;
+  const int c = sv.rcons[e];
+  int p = sv.rprod[e];
+  const int need = q - ((p - c) & 255);
+  if (need <= 0) return;
   Mt rng(sv, e);
-  typename Env::State s;
-  StepOut so;
-  Env::reset(sv, s, &rng, so);
-  Env::store_rec(sv, e, s);
+#pragma unroll 1
+  for (int i = 0; i < need; ++i) {
+    typename Env::State s;
+    StepOut so;
+    Env::reset(sv, s, &rng, so);
+    Env::store_rec(sv, e, p & (q - 1), s);
+    ++p;
+  }
   rng.save(sv, e);
-  sv.rstat[e] = 1;
+  sv.rprod[e] = (uint8_t)p;
 }
 
 // Fused rollout: T sync steps of all N envs in one launch; state stays in registers, the
 // action stream [T,N] is read and the outputs [T,N,...] written once each.  Record envs:
-// the first reset of an env takes its record, later ones draw in place, and the record is
-// redrawn before the kernel ends -- the draw order per env is the sequential one.
+// resets take the env's ring records first (the earlier draws), then draw in place, and the
+// ring is refilled before the kernel ends -- the draw order per env is the sequential one.
 template <class Env>
 __global__ void __launch_bounds__(kBlock)
 rollout_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ actions,
@@ -520,16 +518,14 @@ rollout_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ a
   int flags = 0, mt_idx = 0;
   constexpr bool kRng = Env::kRngInReset || Env::kRngInStep;
   constexpr bool kRec = UsesRec<Env>::value;
-  typename Env::State rec;
-  bool have_rec = false;
+  int rc = 0, rp = 0;  // record ring counters (consumed / produced)
   if (active) {
     flags = sv.flags[eid];
     if (kRng) mt_idx = sv.mt_idx[eid];
     Env::load(sv, eid, s);
     if constexpr (kRec) {
-      if (sv.rstat[eid] != 1) __trap();
-      Env::load_rec(sv, eid, rec);
-      have_rec = true;
+      rc = sv.rcons[eid];
+      rp = sv.rprod[eid];
     }
   }
   typename Env::Act a_next = typename Env::Act();
@@ -550,10 +546,10 @@ rollout_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ a
         } else {
           cur = 0;
           done = 0;
-          if (have_rec) {
-            s = rec;
+          if (((rp - rc) & 255) != 0) {  // the ring first: its records are the earlier draws
+            Env::load_rec(sv, eid, rc & (sv.rec_q - 1), s);
             so.reward = 0.0f;
-            have_rec = false;
+            ++rc;
           } else {
             Mt rng(sv, eid, mt_idx);
             Env::reset(sv, s, &rng, so);
@@ -562,8 +558,7 @@ rollout_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ a
         }
         flags = (cur << 1) | done;
       } else {
-        int rstat = 0;
-        env_step<Env>(sv, eid, flags, s, a, false, so, mt_idx, rec, rstat);
+        env_step<Env>(sv, eid, flags, s, a, false, so, mt_idx, 0);
       }
       write_common(ov, row, eid + sv.env_id_offset, flags >> 1, flags & 1, so.reward,
                    sv.max_steps);
@@ -580,13 +575,22 @@ rollout_kernel(StateView sv, OutView ov, const typename Env::Act* __restrict__ a
     Env::store(sv, eid, s);
     sv.flags[eid] = flags;
     if constexpr (kRec) {
-      if (!have_rec) {  // consumed: draw the next record now
+      const int q = sv.rec_q;
+      const int need = q - ((rp - rc) & 255);
+      if (need > 0) {  // leave the ring full, like refill_kernel
         Mt rng(sv, eid, mt_idx);
-        StepOut so;
-        Env::reset(sv, rec, &rng, so);
+#pragma unroll 1
+        for (int i = 0; i < need; ++i) {
+          typename Env::State r;
+          StepOut so;
+          Env::reset(sv, r, &rng, so);
+          Env::store_rec(sv, eid, rp & (q - 1), r);
+          ++rp;
+        }
         mt_idx = rng.idx;
-        Env::store_rec(sv, eid, rec);
       }
+      sv.rcons[eid] = (uint8_t)rc;
+      sv.rprod[eid] = (uint8_t)rp;
     }
     if (kRng) sv.mt_idx[eid] = mt_idx;
   }
@@ -604,7 +608,6 @@ struct LaunchArgs {
   cudaStream_t stream;
   const PeerView* peers;  // device pointer; non-NULL = fused peer exchange epilogue
   const void* next_action;  // step chains: action row of the following step (L2 prefetch)
-  int refill_code;        // refill only: rstat value to match (0 = every record not full)
 };
 typedef cudaError_t (*launch_fn)(const LaunchArgs&);
 
@@ -676,7 +679,7 @@ cudaError_t launch_rollout(const LaunchArgs& a) {
 template <class Env>
 cudaError_t launch_refill(const LaunchArgs& a) {
   int grid = (a.sv.n_envs + kBlock - 1) / kBlock;
-  refill_kernel<Env><<<grid, kBlock, 0, a.stream>>>(a.sv, a.refill_code);
+  refill_kernel<Env><<<grid, kBlock, 0, a.stream>>>(a.sv);
   return cudaGetLastError();
 }
 

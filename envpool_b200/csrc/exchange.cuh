@@ -29,9 +29,9 @@
 // consumed (the sender never waits for the transfer of the previous step).  Slot t % D may be
 // overwritten by step t + D only after every rank has released step t; a rank releases by
 // publishing ack_flag (its wait kernel for step u first stores "steps < u are consumed" into
-// ack_flag[rank] of every rank).  `credit_kernel` (one warp, in front of step t) holds the
-// stream until every ack >= t - D + 1.  With step/wait strictly alternating on one stream
-// the credit is always there already.
+// ack_flag[rank] of every rank).  The pushing CTAs check the credit (`peer_credit`: every
+// ack >= t - D + 1) right before their first peer store -- a local L2 read that is almost
+// always true at once; with step/wait strictly alternating on one stream it always is.
 //
 // Why not ncclAllGather: measured 35 us per call for the 2.75 MB CartPole slab on 2 GPUs
 // (protocol latency), against ~4 us for the step itself; the peer stores cost the NVLink time
@@ -60,8 +60,11 @@ struct PeerView {
   char* slice[kMaxPeers];                // slot[s][rank] in the allocation of rank g
   unsigned long long* flag[kMaxPeers];   // &data_flag[rank] in the allocation of rank g
   ExchangeCtl* ctl;                      // this rank's control block
+  const unsigned long long* ack;         // this rank's ack_flag[world] (peers write it)
+  long long timeout_ns;                  // bound of the credit wait
   int world;
   int rank;
+  int depth;                             // ring slots
   // wire columns (forwarded to peers): byte offset in the slice and bytes per row
   int ncols;
   int col_rb[kMaxCols];
@@ -84,6 +87,38 @@ __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned l
 // elapsed_step << 2 | trunc << 1 | done: everything the common columns are made of
 __device__ __forceinline__ int32_t pack_wire(int cur, int done, int trunc) {
   return (cur << 2) | (trunc << 1) | done;
+}
+
+// Credit of step t (t = ctl->seq, the steps this rank has pushed so far): slot t % D may be
+// overwritten on rank g once g has released step t - D, i.e. ack_flag[g] >= t - D + 1.  The
+// flags live in THIS rank's memory (peers store into them), so the poll is a local L2 read
+// and, with any slack in the ring, true on the first look.  Lanes 0..world-1 of the CTA poll;
+// bounded like every wait of the exchange.  ctl->seq cannot change while a CTA is here: it
+// is bumped by the last CTA to finish, and this one has not finished.  Deadlock-free: the
+// releases a rank waits for are published by kernels of OTHER GPUs, and its own release of
+// step t - D precedes this kernel in stream / graph order.
+__device__ __forceinline__ void peer_credit(const PeerView* __restrict__ pv) {
+  const int tid = threadIdx.x;
+  if (tid < pv->world) {  // own release included: the local consumer may sit on another stream
+    const unsigned long long t = pv->ctl->seq;
+    if (t >= (unsigned long long)pv->depth) {
+      const unsigned long long need = t - pv->depth + 1;
+      long long t0 = 0;
+      bool timing = false;
+      while (ld_acquire_sys(pv->ack + tid) < need) {
+        long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (!timing) {
+          t0 = t1;
+          timing = true;
+        } else if (t1 - t0 > pv->timeout_ns) {
+          atomicExch(&pv->ctl->error, 1);
+          break;
+        }
+        __nanosleep(32);
+      }
+    }
+  }
 }
 
 // Last-block-done publication: every CTA fences its peer stores at system scope before it
@@ -132,6 +167,7 @@ __device__ __forceinline__ void peer_forward_rows(const PeerView* __restrict__ p
     s_off[tid] = pv->col_off[tid] + row0 * rb;
   }
   if (tid < world) s_peer[tid] = pv->slice[tid];
+  peer_credit(pv);  // every peer has released the slot these rows go into
   __syncthreads();  // tables ready; all rows of this CTA are written (by this CTA)
   if (tid == 0) {
     int acc = 0;

@@ -756,10 +756,16 @@ namespace {
 constexpr int kThreadBlock = 64;
 
 // One launch = T sync steps of `n` batch rows; ONE THREAD PER ENV (row).
+//
+// `lane_shift` (experiment, default 0): only every (1 << lane_shift)-th lane of a warp carries
+// an env -- see hc_lane_shift() for why spreading a small batch over more warps does not pay.
 __global__ void __launch_bounds__(kThreadBlock)
 hc_thread_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict__ action,
-                 const int32_t* __restrict__ env_ids, int n, int force_reset, int T) {
-  const int row = blockIdx.x * kThreadBlock + threadIdx.x;
+                 const int32_t* __restrict__ env_ids, int n, int force_reset, int T,
+                 int lane_shift) {
+  const int tid = blockIdx.x * kThreadBlock + threadIdx.x;
+  if (tid & ((1 << lane_shift) - 1)) return;
+  const int row = tid >> lane_shift;
   if (row >= n) return;
   const int eid = env_ids ? env_ids[row] : row;
   const int64_t N = sv.n_envs;
@@ -864,6 +870,20 @@ MjcPool* mjc_pool_create(int num_envs, int precision, int frame_skip, double ctr
 void mjc_pool_destroy(MjcPool* m) { delete m; }
 int mjc_state_reals(const MjcPool*) { return kStateReals; }
 
+// Lane spreading of the thread kernel (one env per 2^shift lanes).  Measured on B200
+// (profiles/r2_summary.md): it does NOT pay -- 4096 envs: 272 / 262 / 290 / 371 us per step at
+// shift 0 / 1 / 2 / 3, 32768 envs: 545 / 861 / 1291 / 2019 -- because the kernel is bound by
+// its local-memory traffic (6.5 KB of spilled constraint rows per env, 226 MB of DRAM traffic
+// per 32768-env launch): with idle lanes in between, every spilled word still moves a full
+// 32-byte sector.  Default 0; ENVPOOL_B200_HC_LANE_SHIFT (0..5) keeps the experiment runnable.
+static int hc_lane_shift(int) {
+  static const int forced = [] {
+    const char* e = getenv("ENVPOOL_B200_HC_LANE_SHIFT");
+    return e ? atoi(e) : -1;
+  }();
+  return (forced >= 0 && forced <= 5) ? forced : 0;
+}
+
 cudaError_t mjc_launch_step(MjcPool* m, const StateView& sv, const OutView& ov,
                             const double* d_action, const int32_t* d_env_ids, int n,
                             int force_reset, cudaStream_t stream) {
@@ -872,9 +892,10 @@ cudaError_t mjc_launch_step(MjcPool* m, const StateView& sv, const OutView& ov,
     hc_kernel<<<grid, kWarps * 32, 0, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
                                                 force_reset, 1);
   } else {
-    int grid = (n + kThreadBlock - 1) / kThreadBlock;
+    const int sh = hc_lane_shift(n);
+    int grid = (int)((((int64_t)n << sh) + kThreadBlock - 1) / kThreadBlock);
     hc_thread_kernel<<<grid, kThreadBlock, 0, stream>>>(sv, ov, m->prm, d_action, d_env_ids,
-                                                        n, force_reset, 1);
+                                                        n, force_reset, 1, sh);
   }
   return cudaGetLastError();
 }
@@ -885,9 +906,10 @@ cudaError_t mjc_launch_rollout(MjcPool* m, const StateView& sv, const OutView& o
     int grid = (n + kWarps - 1) / kWarps;
     hc_kernel<<<grid, kWarps * 32, 0, stream>>>(sv, ov, m->prm, d_actions, nullptr, n, 0, T);
   } else {
-    int grid = (n + kThreadBlock - 1) / kThreadBlock;
+    const int sh = hc_lane_shift(n);
+    int grid = (int)((((int64_t)n << sh) + kThreadBlock - 1) / kThreadBlock);
     hc_thread_kernel<<<grid, kThreadBlock, 0, stream>>>(sv, ov, m->prm, d_actions, nullptr, n,
-                                                        0, T);
+                                                        0, T, sh);
   }
   return cudaGetLastError();
 }

@@ -67,65 +67,30 @@ def test_two_ranks_one_device(task, kw, n_act):
         p.close()
 
 
-@pytest.mark.parametrize("task,kw,n_act,tol", [
-    ("CartPole", dict(max_episode_steps=9), 2, 1e-6),
-    ("Catch", dict(), 3, 0.0),
-])
-def test_captured_exchange_chain_runs_ahead_of_the_waits(task, kw, n_act, tol):
+@pytest.mark.parametrize("task", ["CartPole", "Catch"])
+def test_captured_exchange_chain_runs_ahead_of_the_waits(task):
     """epb_step_exchange_many_device: K exchanged steps in one CUDA graph, the waits on a
     parallel branch, so step t+1..t+depth-2 compute and push while the batch of step t is
     still arriving (ring slots + credit / ack flags).  After every chain both ranks hold the
-    oracle's full batch; the un-captured chain gives the same bytes."""
-    import torch
+    oracle's full batch; the un-captured chain gives the same bytes.
 
-    from envpool_b200._capi import CPool
-    from oracle.oracle_lib import OraclePool
+    Runs in a subprocess (tests/exchange_chain_check.py) with CUDA_DEVICE_MAX_CONNECTIONS=32:
+    two ranks played by ONE process on ONE device share that process's hardware launch queues,
+    and a wait kernel spinning at the head of a queue that also carries the other rank's step
+    kernels is a false dependency the real deployment (one process per GPU) cannot have --
+    there a rank only ever waits for kernels of other processes.  The cross-process flavour of
+    the same chain is tests/test_gpu_sharded.py."""
+    import os
+    import subprocess
+    import sys
 
-    n, world, T = 3000, 2, 24
-    rng = np.random.default_rng(4)
-    acts = rng.integers(0, n_act, size=(T, world * n)).astype(np.int32)
-    d_acts = [torch.from_numpy(np.ascontiguousarray(acts[:, r * n:(r + 1) * n])).cuda()
-              for r in range(world)]
-
-    def make():
-        pools = [CPool(task, n, seed=3, env_id_offset=r * n, **kw) for r in range(world)]
-        for r, p in enumerate(pools):
-            p.exchange_init(world, r)
-        bases = [p.exchange_base() for p in pools]
-        for p in pools:
-            p.exchange_attach(bases)
-        for p in pools:
-            p.step_exchange(None)
-        for p in pools:
-            p.exchange_wait()
-        return pools
-
-    pools, plain = make(), make()
-    orc = OraclePool(task, world * n, seed=3, **kw)
-    orc.reset()
-    assert pools[0].exchange_depth >= 3
-    t = 0
-    for K in (8, 8, 4, 12, 8):
-        ptrs = [p.step_exchange_many(d_acts[r], t % T, K, use_graph=True)
-                for r, p in enumerate(pools)]
-        ptrs2 = [p.step_exchange_many(d_acts[r], t % T, K, use_graph=False)
-                 for r, p in enumerate(plain)]
-        for k in range(K):
-            want = orc.step(acts[(t + k) % T])
-        t += K
-        for p in pools + plain:
-            p.sync()
-        for r, p in enumerate(pools):
-            got = {k: v.reshape((world * n,) + tuple(v.shape[2:])).cpu().numpy()
-                   for k, v in _views(p, ptrs[r], world, n).items()}
-            assert_batch_equal(got, want, task, tol, f"{task} rank {r} after {t} steps")
-            got2 = {k: v.reshape((world * n,) + tuple(v.shape[2:])).cpu().numpy()
-                    for k, v in _views(plain[r], ptrs2[r], world, n).items()}
-            assert_batch_equal(got2, got, task, 0.0, f"{task} rank {r}: direct vs captured")
-    for p in pools + plain:
-        steps, timed_out = p.exchange_status()
-        assert steps == 1 + t and not timed_out
-        p.close()
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32",
+               ENVPOOL_B200_EXCHANGE_TIMEOUT_S="20")
+    out = subprocess.run([sys.executable, os.path.join(here, "exchange_chain_check.py"), task],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "CHAIN OK" in out.stdout, out.stdout[-3000:]
 
 
 def test_exchange_errors_and_single_rank():

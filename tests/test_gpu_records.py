@@ -1,13 +1,14 @@
-"""GPU: the reset-ahead records of classic_control (csrc/common.cuh StateView::rec).
+"""GPU: the reset-ahead record rings of classic_control (csrc/common.cuh StateView::rec).
 
 An env's Reset() (cartpole.h:82-90, pendulum.h:77-84, acrobot.h:94-103,
 mountain_car.h:76-82) is a pure function of its own mt19937 stream, so the engine draws each
-env's NEXT initial state ahead of time (refill_kernel) and the step kernel's auto-reset takes
-it with a load.  The order of draws per env is unchanged, hence every trajectory must stay
-the one the reference produces.  These tests stress what the record adds: resets on
-consecutive steps, the CUDA-graph chain in which refill(t) runs beside step t+1 and step t+2
-waits for it, repeated forced resets, partial-id steps, and the fused rollout consuming and
-redrawing records."""
+env's NEXT initial states ahead of time into a ring (refill_kernel) and the step kernel's
+auto-reset takes the next record with a load.  Records are produced and consumed in order,
+hence every trajectory must stay the one the reference produces.  These tests stress what the
+ring adds: the tightest legal reset spacing against small rings and long refill periods
+(the bound rec_q >= refill_every + 2 of capi.cu run_chain), the CUDA-graph chain in which a
+refill runs beside the following steps, repeated forced resets, partial-id steps, and the
+fused rollout consuming and redrawing records."""
 import numpy as np
 import pytest
 
@@ -19,6 +20,42 @@ CLASSIC = ["CartPole", "Pendulum", "Acrobot", "MountainCar", "MountainCarContinu
 
 def _outputs(pool):
     return {k: v.cpu().numpy() for k, v in pool.outputs_torch().items()}
+
+
+@pytest.mark.parametrize("ring", [None, (4, 2), (8, 6), (16, 14)])
+def test_ring_bound_under_the_tightest_reset_spacing(capi, monkeypatch, ring):
+    """max_episode_steps = 1: every env resets every second step, the fastest a free-running
+    env can consume records.  Default ring (16 records, refill every 8 steps), the smallest
+    (4 / 2), 8 / 6 and the longest period a 16-ring allows (14): captured chains against the oracle."""
+    import torch
+    from oracle.oracle_lib import OraclePool
+
+    if ring:
+        monkeypatch.setenv("ENVPOOL_B200_REC_Q", str(ring[0]))
+        monkeypatch.setenv("ENVPOOL_B200_REFILL_EVERY", str(ring[1]))
+    N, T = 5000, 64
+    rng = np.random.default_rng(12)
+    pool = capi.CPool("CartPole", N, seed=2, max_episode_steps=1)
+    orc = OraclePool("CartPole", N, seed=2, max_episode_steps=1)
+    if ring:
+        assert pool.state_layout()["rec_q"] == ring[0]
+    pool.reset_device()
+    orc.reset()
+    acts = random_actions("CartPole", rng, (T, N))
+    d_acts = torch.from_numpy(acts).cuda()
+    t = 0
+    for K in (64, 37, 64, 5, 64):
+        pool.step_many_device(d_acts, t % T, K, use_graph=True)
+        for k in range(K):
+            want = orc.step(acts[(t + k) % T])
+        t += K
+        pool.sync()
+        assert_batch_equal(_outputs(pool), want, "CartPole", 1e-6, f"ring={ring} after {t}")
+    for k in range(9):            # direct launches: refill every refill_every-th one
+        pool.step_device(d_acts[k])
+        want = orc.step(acts[k])
+    pool.sync()
+    assert_batch_equal(_outputs(pool), want, "CartPole", 1e-6, f"ring={ring} direct")
 
 
 @pytest.mark.parametrize("ms", [1, 2, 3, 17])
@@ -65,8 +102,8 @@ def test_graph_chain_matches_oracle_with_dense_resets(capi, task, ms):
 
 @pytest.mark.parametrize("task", ["CartPole", "Pendulum"])
 def test_repeated_forced_resets_and_partial_ids(capi, task):
-    """reset() twice in a row consumes two records (the second one refilled in between);
-    partial-id steps and resets only touch their own records."""
+    """Forced resets consume one record per call, whatever the env's state; partial-id steps
+    and resets only touch their own rings."""
     from oracle.oracle_lib import OraclePool
 
     ms, iopt = REGISTERED[task]
@@ -74,7 +111,7 @@ def test_repeated_forced_resets_and_partial_ids(capi, task):
     rng = np.random.default_rng(5)
     pool = capi.CPool(task, N, seed=3, max_episode_steps=4, iopt=iopt)
     orc = OraclePool(task, N, seed=3, max_episode_steps=4, iopt=iopt)
-    for r in range(3):
+    for r in range(21):   # more forced resets in a row than a ring holds (16): refills in between
         assert_batch_equal(pool.reset(), orc.reset(), task, 1e-6, f"reset #{r}")
     for t in range(12):
         sub = np.sort(rng.choice(N, size=300, replace=False)).astype(np.int32)
@@ -115,14 +152,11 @@ def test_rollout_then_steps_share_the_record_stream(capi, task):
             assert_batch_equal(pool.step(a), orc.step(a), task, 1e-6, f"step after rollout {t}")
 
 
-@pytest.mark.parametrize("spec", ["0", "1"])
-def test_both_record_load_variants(capi, monkeypatch, spec):
-    """The record is fetched only by the resetting lanes (default) or speculatively with the
-    state by every lane (ENVPOOL_B200_REC_SPEC=1, read at pool creation); same trajectories."""
+def test_large_batch_prefix(capi):
+    """A 300000-env pool (state + rings beyond L2 residency): a prefix against the oracle."""
     import torch
     from oracle.oracle_lib import OraclePool
 
-    monkeypatch.setenv("ENVPOOL_B200_REC_SPEC", spec)
     N, P = 300000, 4096
     pool = capi.CPool("CartPole", N, seed=1, max_episode_steps=6)
     orc = OraclePool("CartPole", P, seed=1, max_episode_steps=6)

@@ -41,11 +41,11 @@ def load_both(pool, orc, tables, force_done):
     n = tables.shape[0]
     st["mt"][:] = tables.reshape(n, 78, 8).transpose(1, 0, 2)
     st["mt_idx"][:] = 0
-    if "rstat" in st:
-        # classic_control keeps each env's NEXT initial state in a reset-ahead record drawn
-        # from the table before the crafting; marking it not-full makes epb_state_import
-        # redraw it from the crafted table (the refill path), as the oracle's next Reset will
-        st["rstat"][:] = 0
+    if "rprod" in st:
+        # classic_control keeps each env's NEXT initial states in a ring of records drawn from
+        # the table before the crafting; emptying the ring makes epb_state_import redraw all
+        # of them from the crafted table (the refill path), as the oracle's next Resets will
+        st["rprod"][:] = st["rcons"]
     if force_done:
         st["flags"][:] = st["flags"] | 1
     pool.state_import(blob)
