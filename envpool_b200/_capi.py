@@ -38,6 +38,7 @@ ABI_SYMBOLS = [
     "epb_exchange_attach_ipc", "epb_step_exchange_device", "epb_exchange_wait",
     "epb_exchange_status", "epb_exchange_slice_bytes", "epb_exchange_depth",
     "epb_step_many_timed", "epb_step_exchange_many_device", "epb_fp64_peak_gflops",
+    "epb_hc_model",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -122,12 +123,23 @@ def load_library() -> ctypes.CDLL:
                                       ctypes.POINTER(ctypes.c_float)]
     L.epb_step_exchange_many_device.argtypes = [vp, vp, ci, ci, ci, ci, vp, pp]
     L.epb_fp64_peak_gflops.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+    L.epb_hc_model.restype = ctypes.c_int64
+    L.epb_hc_model.argtypes = [vp, ctypes.c_int64]
     _lib = L
     return L
 
 
 class EpbError(RuntimeError):
     pass
+
+
+def hc_model_blob() -> bytes:
+    """The compiled HalfCheetah model (hcm::HcModel) as bytes; host only, no GPU needed."""
+    L = load_library()
+    n = int(L.epb_hc_model(None, 0))
+    buf = ctypes.create_string_buffer(n)
+    L.epb_hc_model(buf, n)
+    return buf.raw
 
 
 def fp64_peak_gflops(device: int = 0) -> float:

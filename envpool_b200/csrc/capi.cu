@@ -555,6 +555,15 @@ int host_submit(epb_pool* p, const void* action, const int32_t* env_ids, int n,
   p->stage_flip ^= 1;
   // the staging pair alternates; wait until the copy that last used this half is done
   EPB_CUDA(cudaEventSynchronize(p->h_stage_ev[f]));
+  // The action goes first: its staging copy and H2D are on the critical path of the step,
+  // and the env-id check below (a 4N-byte compare) then runs while the copy is in flight.
+  if (!force_reset) {
+    if (!action) return fail(EPB_ERR_INVALID, "action is NULL");
+    size_t bytes = (size_t)p->act.row_bytes * n;
+    memcpy(p->h_action[f], action, bytes);
+    EPB_CUDA(cudaMemcpyAsync(p->d_action, p->h_action[f], bytes, cudaMemcpyHostToDevice,
+                             p->stream));
+  }
   bool identity = (n == p->N);
   if (env_ids) {
     // fast path: the usual sync-mode call passes env_id == arange(N) (python/envpool.py
@@ -566,7 +575,10 @@ int host_submit(epb_pool* p, const void* action, const int32_t* env_ids, int n,
       identity = false;
       const unsigned un = (unsigned)p->N;
       for (int i = 0; i < n; ++i) ok &= (unsigned)env_ids[i] < un;
-      if (!ok) return fail(EPB_ERR_INVALID, "env_id out of range");
+      if (!ok) {
+        cudaEventRecord(p->h_stage_ev[f], p->stream);  // the action copy may still be in flight
+        return fail(EPB_ERR_INVALID, "env_id out of range");
+      }
     }
   } else if (n != p->N) {
     identity = false;  // rows 0..n-1 of a partial batch: ids are 0..n-1
@@ -581,13 +593,6 @@ int host_submit(epb_pool* p, const void* action, const int32_t* env_ids, int n,
     EPB_CUDA(cudaMemcpyAsync(p->d_ids, p->h_ids[f], sizeof(int32_t) * n,
                              cudaMemcpyHostToDevice, p->stream));
     d_ids = p->d_ids;
-  }
-  if (!force_reset) {
-    if (!action) return fail(EPB_ERR_INVALID, "action is NULL");
-    size_t bytes = (size_t)p->act.row_bytes * n;
-    memcpy(p->h_action[f], action, bytes);
-    EPB_CUDA(cudaMemcpyAsync(p->d_action, p->h_action[f], bytes, cudaMemcpyHostToDevice,
-                             p->stream));
   }
   EPB_CUDA(cudaEventRecord(p->h_stage_ev[f], p->stream));
   // the step kernel alone; the refill of the records it consumed goes BEHIND the D2H copy
@@ -1571,6 +1576,7 @@ int epb_fp64_peak_gflops(int device, double* gflops_out) {
   return EPB_OK;
 }
 
+int64_t epb_hc_model(void* dst, int64_t cap) { return mjc_model_blob(dst, cap); }
 int64_t epb_launch_count(const epb_pool* p) { return p ? p->launches : 0; }
 int epb_bytes_per_env_step(const epb_pool* p) { return p ? p->bytes_per_step : 0; }
 

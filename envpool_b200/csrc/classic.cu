@@ -124,8 +124,19 @@ __device__ __forceinline__ void store_rec_real(const StateView& sv, int eid, int
     }
   }
 }
+template <typename R, int NR>
+__device__ __forceinline__ void prefetch_rec_real(const StateView& sv, int eid, int slot) {
+  constexpr int kBytes = NR * (int)sizeof(R);
+  const char* p = static_cast<const char*>(sv.rec) +
+                  ((int64_t)eid * sv.rec_q + slot) * kBytes;
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 #define EPB_REC_RESET_MEMBERS                                                               \
   static constexpr bool kRecReset = true;                                                   \
+  static __device__ __forceinline__ void prefetch_rec(const StateView& sv, int e, int slot) { \
+    prefetch_rec_real<typename std::remove_reference<decltype(State().v[0])>::type,         \
+                      (int)(sizeof(State) / sizeof(State().v[0]))>(sv, e, slot);            \
+  }                                                                                         \
   static __device__ __forceinline__ void load_rec(const StateView& sv, int e, int slot,     \
                                                   State& s) {                               \
     load_rec_real(sv, e, slot, s);                                                          \

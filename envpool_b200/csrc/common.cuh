@@ -377,6 +377,10 @@ __device__ __forceinline__ void env_step(const StateView& sv, int eid, int& flag
       // issued NOW, ahead of the step arithmetic that hides its latency
       Env::load_rec(sv, eid, rcons & (sv.rec_q - 1), rec);
       sv.rcons[eid] = (uint8_t)(rcons + 1);
+      // ... and ask L2 for the record AFTER this one (fire and forget): the env's next reset is
+      // >= 2 and typically ~20 steps away, so whatever has streamed through L2 since the ring
+      // was written, that reset finds its 32 bytes on chip.  One request per resetting lane.
+      Env::prefetch_rec(sv, eid, (rcons + 1) & (sv.rec_q - 1));
     }
     typename Env::State s1 = s;
     StepOut so1 = so;

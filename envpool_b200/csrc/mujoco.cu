@@ -18,6 +18,7 @@
 // PARITY: unpinned against MuJoCo itself (absent from the image); pinned against the CPU
 // restatement of the same pipeline (tests/ only).  See DESIGN.md "HalfCheetah".
 #include "mujoco.cuh"
+#include "mujoco_model.h"
 
 #include <cmath>
 #include <cstdio>
@@ -29,25 +30,12 @@ namespace epb {
 
 namespace {
 
-constexpr int NV = 9, NB = 7, NG = 8, NU = 6;
+using hcm::NV; using hcm::NB; using hcm::NG; using hcm::NU;
+using hcm::MINVAL; using hcm::MINIMP; using hcm::MAXIMP;
+using hcm::HcModel; using hcm::LegModel;
 constexpr int MAXROW = 6 + 3 * 16;  // 6 limits + 16 contacts x 3 merged pyramid rows
 constexpr int kStateReals = 32;     // qpos[9] qvel[9] warm[9] norm_saved norm_has pad[3]
 constexpr int kWarps = 4;           // envs per CTA
-constexpr double MINVAL = 1e-15, MINIMP = 0.0001, MAXIMP = 0.9999;
-
-struct HcModel {
-  double mass[NB], comx[NB], comz[NB], iyy[NB], bposx[NB], bposz[NB];
-  double armature[NV], damping[NV], stiffness[NV], rlo[NV], rhi[NV];
-  double gear[NU];
-  double gposx[NG], gposz[NG], gaxx[NG], gaxz[NG], ghalf[NG];
-  double dof_invweight0[NV], body_invw_tran[NB];
-  double grad, timestep, gravity, mu, meaninertia, tolerance;
-  double solref[2], solimp[3], solref_limit[2], solimp_limit[3];
-  int parent[NB], depth[NB], gbody[NG];
-  int chain_len[NB], chain[NB][4];  // hinge dofs from the root to the body, in order
-  int chainmask[NB];                // bit d set iff hinge dof d is on the body's chain
-  int max_iter, ls_iter;
-};
 
 __constant__ HcModel cm;
 
@@ -844,11 +832,155 @@ hc_thread_kernel(StateView sv, OutView ov, HcParams prm, const double* __restric
 }
 
 }  // namespace
+}  // namespace epb
+
+#include "mujoco_pair.cuh"
+
+namespace epb {
+namespace {
+
+constexpr int kPairBlock = 64;  // threads per CTA = 32 envs
+constexpr int kPairKsMin = 9;   // fewest constraint rows per lane ever held in shared memory
+
+// One launch = T sync steps of `n` batch rows; TWO LANES PER ENV (mujoco_pair.cuh): lane
+// 2*row is the back leg (and does everything that exists once per env: RNG, reward, the
+// common columns), lane 2*row + 1 the front leg.  Dynamic shared memory: the first `ks`
+// constraint rows of every lane, interleaved by thread.
+__global__ void __launch_bounds__(kPairBlock)
+hc_pair_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict__ action,
+               const int32_t* __restrict__ env_ids, int n, int force_reset, int T, int ks) {
+  extern __shared__ double srows[];
+  __shared__ LegModel lm[2];
+  if (threadIdx.x < 2) hcm::leg_model_of(cm, threadIdx.x, &lm[threadIdx.x]);
+  __syncthreads();
+  const int tid = blockIdx.x * kPairBlock + threadIdx.x;
+  const int row = tid >> 1, side = tid & 1;
+  if (row >= n) return;  // both lanes of a pair leave together
+  const int eid = env_ids ? env_ids[row] : row;
+  const int64_t N = sv.n_envs;
+  double* st = static_cast<double*>(sv.rstate) + eid;
+  double ovf[(hcp::MAXR - kPairKsMin) * hcp::NF];
+  hcp::Ctx c;
+  c.side = side;
+  c.pm = 3u << (threadIdx.x & 30);
+  c.chan = nullptr;
+  c.srow = srows + threadIdx.x;
+  c.sstride = kPairBlock;
+  c.ks = ks;
+  c.ovf = ovf;
+  const LegModel& L = lm[side];
+  const int l0 = 3 + 3 * side;  // first dof of this lane's leg
+  hcp::PairState s;
+  int flags = sv.flags[eid];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    s.qr[i] = st[i * N];
+    s.vr[i] = st[(NV + i) * N];
+    s.wr[i] = st[(2 * NV + i) * N];
+    s.ql[i] = st[(l0 + i) * N];
+    s.vl[i] = st[(NV + l0 + i) * N];
+    s.wl[i] = st[(2 * NV + l0 + i) * N];
+  }
+  for (int t = 0; t < T; ++t) {
+    const int64_t orow = (int64_t)t * ov.t_stride_rows + row;
+    int done = flags & 1, cur = flags >> 1;
+    const bool reset = force_reset || done;
+    double xv = 0, ctrl_cost = 0, x_after = 0;
+    float reward = 0.0f;
+    if (reset) {
+      // HalfCheetahEnv::Reset (half_cheetah.h:105-134): the back-leg lane draws, both keep
+      // their part
+      cur = 0;
+      done = 0;
+      double q9[NV], v9[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) q9[i] = v9[i] = 0.0;
+      if (side == 0) {
+        Mt rng(sv, eid);
+        double saved = st[27 * N];
+        bool has = st[28 * N] != 0.0;
+        rng.uniform_real_batch<NV>(-prm.reset_noise_scale, prm.reset_noise_scale, q9);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) q9[i] = 0.0 + q9[i];
+        for (int i = 0; i < NV; ++i)
+          v9[i] = 0.0 + hc_normal(rng, saved, has, 0.0, prm.reset_noise_scale);
+        rng.save(sv, eid);
+        st[27 * N] = saved;
+        st[28 * N] = has ? 1.0 : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const double qo = hcp::xch(c, q9[i]), vo = hcp::xch(c, v9[i]);
+        if (side) { q9[i] = qo; v9[i] = vo; }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        s.qr[i] = q9[i];
+        s.vr[i] = v9[i];
+        s.ql[i] = side ? q9[6 + i] : q9[3 + i];
+        s.vl[i] = side ? v9[6 + i] : v9[3 + i];
+        s.wr[i] = 0.0;
+        s.wl[i] = 0.0;
+      }
+    } else {
+      ++cur;
+      const double* act = action + ((int64_t)t * n + row) * NU;
+      double a6[NU];
+#pragma unroll
+      for (int k = 0; k < NU; ++k) a6[k] = act[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s.ctrl[k] = side ? a6[3 + k] : a6[k];
+      const double x_before = s.qr[0];
+      for (int k = 0; k < prm.frame_skip; ++k) hcp::pair_substep(c, cm, L, s);
+      x_after = s.qr[0];
+      // env-layer algebra (half_cheetah.h:147-160) with explicit _rn ops: never FMA-contracted
+#pragma unroll
+      for (int k = 0; k < NU; ++k)
+        ctrl_cost = __dadd_rn(ctrl_cost, __dmul_rn(__dmul_rn(prm.ctrl_cost_weight, a6[k]), a6[k]));
+      const double dt = prm.frame_skip * cm.timestep;
+      xv = (x_after - x_before) / dt;
+      reward = (float)__dsub_rn(__dmul_rn(xv, prm.forward_reward_weight), ctrl_cost);
+      done = (cur >= sv.max_steps);
+    }
+    flags = (cur << 1) | done;
+    double* o = ov.env[0] ? static_cast<double*>(ov.env[0]) + orow * 17 : nullptr;
+    if (side == 0) {
+      write_common(ov, orow, eid + sv.env_id_offset, cur, done, reward, sv.max_steps);
+      if (ov.env[1]) static_cast<double*>(ov.env[1])[orow] = __dmul_rn(xv, prm.forward_reward_weight);
+      if (ov.env[2]) static_cast<double*>(ov.env[2])[orow] = -ctrl_cost;
+      if (ov.env[3]) static_cast<double*>(ov.env[3])[orow] = x_after;
+      if (ov.env[4]) static_cast<double*>(ov.env[4])[orow] = xv;
+      if (o) {
+        o[0] = s.qr[1]; o[1] = s.qr[2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { o[2 + k] = s.ql[k]; o[8 + k] = s.vr[k]; o[11 + k] = s.vl[k]; }
+      }
+    } else if (o) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { o[5 + k] = s.ql[k]; o[14 + k] = s.vl[k]; }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (side == 0) {
+      st[i * N] = s.qr[i];
+      st[(NV + i) * N] = s.vr[i];
+      st[(2 * NV + i) * N] = s.wr[i];
+    }
+    st[(l0 + i) * N] = s.ql[i];
+    st[(NV + l0 + i) * N] = s.vl[i];
+    st[(2 * NV + l0 + i) * N] = s.wl[i];
+  }
+  if (side == 0) sv.flags[eid] = flags;
+}
+
+}  // namespace
 
 struct MjcPool {
   HcParams prm;
   int num_envs;
-  bool warp_variant;  // ENVPOOL_B200_HC_KERNEL=warp selects the warp-per-env kernel
+  int variant;  // 0 = lane pair per env (default), 1 = thread per env, 2 = warp per env
+                // (ENVPOOL_B200_HC_KERNEL=pair|thread|warp)
 };
 
 MjcPool* mjc_pool_create(int num_envs, int precision, int frame_skip, double ctrl_cost_weight,
@@ -864,10 +996,28 @@ MjcPool* mjc_pool_create(int num_envs, int precision, int frame_skip, double ctr
   m->prm.forward_reward_weight = forward_reward_weight;
   m->prm.reset_noise_scale = reset_noise_scale;
   const char* v = getenv("ENVPOOL_B200_HC_KERNEL");
-  m->warp_variant = v && std::string(v) == "warp";
+  m->variant = 0;
+  if (v && std::string(v) == "thread") m->variant = 1;
+  if (v && std::string(v) == "warp") m->variant = 2;
+  if (m->variant == 0 &&
+      cudaFuncSetAttribute(hc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           hcp::MAXR * hcp::NF * kPairBlock * (int)sizeof(double)) != cudaSuccess) {
+    delete m;
+    return nullptr;
+  }
   return m;
 }
 void mjc_pool_destroy(MjcPool* m) { delete m; }
+// The compiled model as a flat blob (hcm::HcModel): host-only, for the CPU tests that run the
+// pair-lane algorithm on host threads.
+int64_t mjc_model_blob(void* dst, int64_t cap) {
+  if (dst && cap >= (int64_t)sizeof(HcModel)) {
+    HcModel tmp;
+    compile_half_cheetah(&tmp);
+    memcpy(dst, &tmp, sizeof(HcModel));
+  }
+  return (int64_t)sizeof(HcModel);
+}
 int mjc_state_reals(const MjcPool*) { return kStateReals; }
 
 // Lane spreading of the thread kernel (one env per 2^shift lanes).  Measured on B200
@@ -884,10 +1034,45 @@ static int hc_lane_shift(int) {
   return (forced >= 0 && forced <= 5) ? forced : 0;
 }
 
+// Rows per lane kept in shared memory: everything (27) while one CTA per SM covers the batch,
+// less as more CTAs have to share an SM (at most 4: the kernel's registers allow no more).
+static int pair_rows_in_smem(int n) {
+  static const int forced = [] {
+    const char* e = getenv("ENVPOOL_B200_HC_PAIR_KS");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced >= kPairKsMin && forced <= hcp::MAXR) return forced;
+  static const int sms = [] {
+    int dev = 0, v = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  const int ctas = (2 * n + kPairBlock - 1) / kPairBlock;
+  int per_sm = (ctas + sms - 1) / sms;
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  const int row_bytes = hcp::NF * kPairBlock * (int)sizeof(double);
+  int ks = (int)((216 * 1024 / per_sm) / row_bytes);
+  ks = ks > hcp::MAXR ? hcp::MAXR : ks;
+  return ks < kPairKsMin ? kPairKsMin : ks;
+}
+
+static void launch_pair(MjcPool* m, const StateView& sv, const OutView& ov, const double* d_action,
+                        const int32_t* d_env_ids, int n, int force_reset, int T,
+                        cudaStream_t stream) {
+  const int ks = pair_rows_in_smem(n);
+  const int grid = (int)((2 * (int64_t)n + kPairBlock - 1) / kPairBlock);
+  const size_t smem = (size_t)ks * hcp::NF * kPairBlock * sizeof(double);
+  hc_pair_kernel<<<grid, kPairBlock, smem, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
+                                                     force_reset, T, ks);
+}
+
 cudaError_t mjc_launch_step(MjcPool* m, const StateView& sv, const OutView& ov,
                             const double* d_action, const int32_t* d_env_ids, int n,
                             int force_reset, cudaStream_t stream) {
-  if (m->warp_variant) {
+  if (m->variant == 0) {
+    launch_pair(m, sv, ov, d_action, d_env_ids, n, force_reset, 1, stream);
+  } else if (m->variant == 2) {
     int grid = (n + kWarps - 1) / kWarps;
     hc_kernel<<<grid, kWarps * 32, 0, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
                                                 force_reset, 1);
@@ -902,7 +1087,9 @@ cudaError_t mjc_launch_step(MjcPool* m, const StateView& sv, const OutView& ov,
 cudaError_t mjc_launch_rollout(MjcPool* m, const StateView& sv, const OutView& ov,
                                const double* d_actions, int T, cudaStream_t stream) {
   int n = sv.n_envs;
-  if (m->warp_variant) {
+  if (m->variant == 0) {
+    launch_pair(m, sv, ov, d_actions, nullptr, n, 0, T, stream);
+  } else if (m->variant == 2) {
     int grid = (n + kWarps - 1) / kWarps;
     hc_kernel<<<grid, kWarps * 32, 0, stream>>>(sv, ov, m->prm, d_actions, nullptr, n, 0, T);
   } else {
