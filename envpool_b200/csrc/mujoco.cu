@@ -219,6 +219,7 @@ void compile_half_cheetah(HcModel* m) {
       }
     m->body_invw_tran[b] = (axx + azz) / 3.0;  // the y row is identically zero (planar)
   }
+  hcm::fill_impedance_constants(m);
 }
 
 // ---------------------------------------------------------------- device: per-warp memory
@@ -840,18 +841,33 @@ namespace epb {
 namespace {
 
 constexpr int kPairBlock = 64;  // threads per CTA = 32 envs
-constexpr int kPairKsMin = 9;   // fewest constraint rows per lane ever held in shared memory
+constexpr int kPairKsMin = 5;   // fewest constraint rows per lane ever held in shared memory
+static_assert(kPairBlock == HCP_SSTRIDE, "row interleave stride = threads per CTA");
+
+// the two LegModel tables in global memory (written once per process, mjc_pool_create): every
+// CTA copies them into shared memory with one coalesced read
+__device__ LegModel g_leg_model[2];
 
 // One launch = T sync steps of `n` batch rows; TWO LANES PER ENV (mujoco_pair.cuh): lane
 // 2*row is the back leg (and does everything that exists once per env: RNG, reward, the
 // common columns), lane 2*row + 1 the front leg.  Dynamic shared memory: the first `ks`
 // constraint rows of every lane, interleaved by thread.
-__global__ void __launch_bounds__(kPairBlock)
+//
+// kMinBlocks = resident CTAs per SM the register allocation must allow: 4 (<= 255 registers, no
+// spills) while 8 warps per SM cover the batch, 8 (<= 128 registers) for batches that need
+// more warps in flight than that to stay in one wave.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kPairBlock, kMinBlocks)
 hc_pair_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict__ action,
                const int32_t* __restrict__ env_ids, int n, int force_reset, int T, int ks) {
   extern __shared__ double srows[];
   __shared__ LegModel lm[2];
-  if (threadIdx.x < 2) hcm::leg_model_of(cm, threadIdx.x, &lm[threadIdx.x]);
+  {
+    const double* src = reinterpret_cast<const double*>(g_leg_model);
+    double* dst = reinterpret_cast<double*>(lm);
+    for (int i = threadIdx.x; i < (int)(2 * sizeof(LegModel) / sizeof(double)); i += kPairBlock)
+      dst[i] = src[i];
+  }
   __syncthreads();
   const int tid = blockIdx.x * kPairBlock + threadIdx.x;
   const int row = tid >> 1, side = tid & 1;
@@ -865,7 +881,6 @@ hc_pair_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict_
   c.pm = 3u << (threadIdx.x & 30);
   c.chan = nullptr;
   c.srow = srows + threadIdx.x;
-  c.sstride = kPairBlock;
   c.ks = ks;
   c.ovf = ovf;
   const LegModel& L = lm[side];
@@ -999,11 +1014,19 @@ MjcPool* mjc_pool_create(int num_envs, int precision, int frame_skip, double ctr
   m->variant = 0;
   if (v && std::string(v) == "thread") m->variant = 1;
   if (v && std::string(v) == "warp") m->variant = 2;
-  if (m->variant == 0 &&
-      cudaFuncSetAttribute(hc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           hcp::MAXR * hcp::NF * kPairBlock * (int)sizeof(double)) != cudaSuccess) {
-    delete m;
-    return nullptr;
+  if (m->variant == 0) {
+    LegModel legs[2];
+    hcm::leg_model_of(host_model, 0, &legs[0]);
+    hcm::leg_model_of(host_model, 1, &legs[1]);
+    const int smem_max = hcp::MAXR * hcp::NF * kPairBlock * (int)sizeof(double);
+    if (cudaMemcpyToSymbol(g_leg_model, legs, sizeof(legs)) != cudaSuccess ||
+        cudaFuncSetAttribute(hc_pair_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_max) != cudaSuccess ||
+        cudaFuncSetAttribute(hc_pair_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_max) != cudaSuccess) {
+      delete m;
+      return nullptr;
+    }
   }
   return m;
 }
@@ -1034,14 +1057,23 @@ static int hc_lane_shift(int) {
   return (forced >= 0 && forced <= 5) ? forced : 0;
 }
 
-// Rows per lane kept in shared memory: everything (27) while one CTA per SM covers the batch,
-// less as more CTAs have to share an SM (at most 4: the kernel's registers allow no more).
-static int pair_rows_in_smem(int n) {
-  static const int forced = [] {
+// Launch shape of the pair kernel for a batch of n rows.  CTAs needed per SM for one wave:
+//   <= 4: the 255-register build; rows per lane in shared memory = everything (27) while one
+//         CTA per SM covers the batch, less as 2-4 CTAs share an SM;
+//   >  4: the 128-register build, 8 CTAs (16 warps) per SM, 5 rows per lane in shared memory.
+// ENVPOOL_B200_HC_PAIR_KS / ENVPOOL_B200_HC_PAIR_MINB (4 | 8) override (A/B switches).
+struct PairShape {
+  int ks, minb;
+};
+static PairShape pair_shape(int n) {
+  static const int forced_ks = [] {
     const char* e = getenv("ENVPOOL_B200_HC_PAIR_KS");
     return e ? atoi(e) : 0;
   }();
-  if (forced >= kPairKsMin && forced <= hcp::MAXR) return forced;
+  static const int forced_minb = [] {
+    const char* e = getenv("ENVPOOL_B200_HC_PAIR_MINB");
+    return e ? atoi(e) : 0;
+  }();
   static const int sms = [] {
     int dev = 0, v = 148;
     cudaGetDevice(&dev);
@@ -1049,22 +1081,31 @@ static int pair_rows_in_smem(int n) {
     return v > 0 ? v : 148;
   }();
   const int ctas = (2 * n + kPairBlock - 1) / kPairBlock;
-  int per_sm = (ctas + sms - 1) / sms;
-  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+  const int need = (ctas + sms - 1) / sms;  // CTAs per SM for a single wave
+  PairShape sh;
+  sh.minb = need > 4 ? 8 : 4;
+  if (forced_minb == 4 || forced_minb == 8) sh.minb = forced_minb;
+  int per_sm = need < 1 ? 1 : (need > sh.minb ? sh.minb : need);
   const int row_bytes = hcp::NF * kPairBlock * (int)sizeof(double);
   int ks = (int)((216 * 1024 / per_sm) / row_bytes);
   ks = ks > hcp::MAXR ? hcp::MAXR : ks;
-  return ks < kPairKsMin ? kPairKsMin : ks;
+  sh.ks = ks < kPairKsMin ? kPairKsMin : ks;
+  if (forced_ks >= kPairKsMin && forced_ks <= hcp::MAXR) sh.ks = forced_ks;
+  return sh;
 }
 
 static void launch_pair(MjcPool* m, const StateView& sv, const OutView& ov, const double* d_action,
                         const int32_t* d_env_ids, int n, int force_reset, int T,
                         cudaStream_t stream) {
-  const int ks = pair_rows_in_smem(n);
+  const PairShape sh = pair_shape(n);
   const int grid = (int)((2 * (int64_t)n + kPairBlock - 1) / kPairBlock);
-  const size_t smem = (size_t)ks * hcp::NF * kPairBlock * sizeof(double);
-  hc_pair_kernel<<<grid, kPairBlock, smem, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
-                                                     force_reset, T, ks);
+  const size_t smem = (size_t)sh.ks * hcp::NF * kPairBlock * sizeof(double);
+  if (sh.minb == 8)
+    hc_pair_kernel<8><<<grid, kPairBlock, smem, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
+                                                          force_reset, T, sh.ks);
+  else
+    hc_pair_kernel<4><<<grid, kPairBlock, smem, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
+                                                          force_reset, T, sh.ks);
 }
 
 cudaError_t mjc_launch_step(MjcPool* m, const StateView& sv, const OutView& ov,

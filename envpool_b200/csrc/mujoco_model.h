@@ -29,7 +29,27 @@ struct HcModel {
   int chain_len[NB], chain[NB][4];  // hinge dofs from the root to the body, in order
   int chainmask[NB];                // bit d set iff hinge dof d is on the body's chain
   int max_iter, ls_iter;
+  // what mj_makeImpedance needs per constraint class ([0] contact, [1] joint limit) that does
+  // not depend on the penetration: clamped solimp dmin / dmax, 1 / width, and solref's
+  // spring-damper  K = 1 / (dmax^2 tc^2 dr^2),  B = 2 / (dmax tc)
+  double imp_dmin[2], imp_dmax[2], imp_invwidth[2], imp_K[2], imp_B[2];
 };
+
+inline void fill_impedance_constants(HcModel* m) {
+  for (int k = 0; k < 2; ++k) {
+    const double* solref = k ? m->solref_limit : m->solref;
+    const double* solimp = k ? m->solimp_limit : m->solimp;
+    const double lo = solimp[0] < MINIMP ? MINIMP : (solimp[0] > MAXIMP ? MAXIMP : solimp[0]);
+    const double hi = solimp[1] < MINIMP ? MINIMP : (solimp[1] > MAXIMP ? MAXIMP : solimp[1]);
+    m->imp_dmin[k] = lo;
+    m->imp_dmax[k] = hi;
+    m->imp_invwidth[k] = 1.0 / solimp[2];
+    const double kd = hi * hi * solref[0] * solref[0] * solref[1] * solref[1];
+    const double bd = hi * solref[0];
+    m->imp_K[k] = 1.0 / (kd < MINVAL ? MINVAL : kd);
+    m->imp_B[k] = 2.0 / (bd < MINVAL ? MINVAL : bd);
+  }
+}
 
 // One leg of the cheetah as the pair-lane kernel sees it: side 0 = back leg (bodies 1-3,
 // dofs 3-5, actuators 0-2, capsules 2-4) + the torso capsule (geom 0); side 1 = front leg

@@ -29,6 +29,7 @@
 #if defined(HCP_HOST)
 #include <cmath>
 #define HCP_FN static inline
+#define HCP_MFN inline
 #define HCP_NOINLINE static
 namespace epb {
 namespace hcp {
@@ -39,6 +40,7 @@ inline void hcp_sincos(double x, double* s, double* c) { *s = std::sin(x); *c = 
 }  // namespace epb
 #else
 #define HCP_FN __device__ __forceinline__
+#define HCP_MFN __device__ __forceinline__
 #define HCP_NOINLINE __device__ __noinline__
 namespace epb {
 namespace hcp {
@@ -66,8 +68,9 @@ struct Ctx {
   int side;       // 0 = back leg + torso capsule, 1 = front leg + head capsule
   unsigned pm;    // device: the two-lane mask of this pair
   void* chan;     // host build: the rendezvous of the two threads
-  double* srow;   // shared-memory rows of this lane: field f of row r at srow[(r*NF+f)*sstride]
-  int sstride;    // = threads per CTA (rows are interleaved by thread: conflict-free)
+  double* srow;   // shared-memory rows of this lane: field f of row r at
+                  // srow[(r*NF+f)*HCP_SSTRIDE], HCP_SSTRIDE = threads per CTA (rows are
+                  // interleaved by thread: conflict-free)
   int ks;         // rows held in shared memory; rows >= ks go to ovf
   double* ovf;    // [MAXR - ks][NF] thread-local overflow
 };
@@ -82,22 +85,38 @@ HCP_FN double xch(const Ctx& c, double v) {
 // own + partner's: bit-identical on both lanes
 HCP_FN double psum(const Ctx& c, double v) { return v + xch(c, v); }
 
-struct RowP {
+// Row r of this lane: in shared memory (r < ks; field f at p[f * stride], stride = threads per
+// CTA, a compile-time constant on the device so every access is an LDS with an immediate
+// offset) or in the thread-local overflow (contiguous).  `with_row` runs `body` on whichever it
+// is; the body is instantiated once per storage class.
+#if defined(HCP_HOST)
+#define HCP_SSTRIDE 1
+#else
+#define HCP_SSTRIDE 64
+#endif
+struct RowS {
   double* p;
-  int st;
+  HCP_MFN double& operator[](int f) const { return p[f * HCP_SSTRIDE]; }
 };
-HCP_FN RowP rowp(const Ctx& c, int r) {
-  RowP q;
+struct RowO {
+  double* p;
+  HCP_MFN double& operator[](int f) const { return p[f]; }
+};
+template <class F>
+HCP_FN void with_row(const Ctx& c, int r, F&& body) {
   if (r < c.ks) {
-    q.p = c.srow + (long long)r * NF * c.sstride;
-    q.st = c.sstride;
+    body(RowS{c.srow + r * (NF * HCP_SSTRIDE)});
   } else {
-    q.p = c.ovf + (r - c.ks) * NF;
-    q.st = 1;
+    body(RowO{c.ovf + (r - c.ks) * NF});
   }
-  return q;
 }
-#define HCP_RF(q, f) (q).p[(f) * (q).st]
+// body(row) for rows 0..n-1 in order: the shared-memory rows, then the (rare) overflow rows
+template <class F>
+HCP_FN void for_rows(const Ctx& c, int n, F&& body) {
+  const int ns = n < c.ks ? n : c.ks;
+  for (int r = 0; r < ns; ++r) body(RowS{c.srow + r * (NF * HCP_SSTRIDE)});
+  for (int r = c.ks; r < n; ++r) body(RowO{c.ovf + (r - c.ks) * NF});
+}
 
 // ---- packed symmetric 3x3: [0]=(0,0) [1]=(1,0) [2]=(1,1) [3]=(2,0) [4]=(2,1) [5]=(2,2) -------
 HCP_FN void symv3(const double* A, const double* x, double* y) {
@@ -185,28 +204,23 @@ HCP_FN void pair_mv(const Ctx& c, const Arrow& H, const double* xr, const double
   for (int l = 0; l < 3; ++l) yl[l] += H.C[l][0] * xr[0] + H.C[l][1] * xr[1] + H.C[l][2] * xr[2];
 }
 
-HCP_FN double row_dot(const RowP& q, const double* xr, const double* xl) {
-  return HCP_RF(q, F_JR + 0) * xr[0] + HCP_RF(q, F_JR + 1) * xr[1] + HCP_RF(q, F_JR + 2) * xr[2] +
-         HCP_RF(q, F_JL + 0) * xl[0] + HCP_RF(q, F_JL + 1) * xl[1] + HCP_RF(q, F_JL + 2) * xl[2];
+template <class Row>
+HCP_FN double row_dot(const Row& q, const double* xr, const double* xl) {
+  return q[F_JR + 0] * xr[0] + q[F_JR + 1] * xr[1] + q[F_JR + 2] * xr[2] +
+         q[F_JL + 0] * xl[0] + q[F_JL + 1] * xl[1] + q[F_JL + 2] * xl[2];
 }
 
-// mj_makeImpedance for one constraint (solimp midpoint 0.5, power 2: MuJoCo's defaults for the
-// entries the XML leaves out)
-HCP_NOINLINE void pair_impedance(const double* solref, const double* solimp, double pos,
-                                 double& imp, double& K, double& B) {
-  double dmin = fmin(MAXIMP, fmax(MINIMP, solimp[0]));
-  double dmax = fmin(MAXIMP, fmax(MINIMP, solimp[1]));
-  double x = fabs(pos) / solimp[2];
-  if (x >= 1) {
-    imp = dmax;
-  } else if (x <= 0) {
-    imp = dmin;
-  } else {
-    double y = x <= 0.5 ? (x * x) / 0.5 : 1 - ((1 - x) * (1 - x)) / 0.5;
-    imp = dmin + y * (dmax - dmin);
-  }
-  K = 1 / fmax(MINVAL, dmax * dmax * solref[0] * solref[0] * solref[1] * solref[1]);
-  B = 2 / fmax(MINVAL, dmax * solref[0]);
+// mj_makeImpedance for one constraint class k (0 = contact, 1 = joint limit): the impedance at
+// penetration `pos` (solimp midpoint 0.5, power 2: MuJoCo's defaults for the entries the XML
+// leaves out).  Everything that does not depend on `pos` -- the clamped dmin / dmax, 1 / width,
+// and the spring-damper K, B of solref -- is precomputed in the model (fill_impedance_constants).
+HCP_FN double pair_imp(const HcModel& cm, int k, double pos) {
+  const double dmin = cm.imp_dmin[k], dmax = cm.imp_dmax[k];
+  const double x = fabs(pos) * cm.imp_invwidth[k];
+  const double u = 1 - x;
+  const double y = x <= 0.5 ? 2 * (x * x) : 1 - 2 * (u * u);
+  const double imp = dmin + y * (dmax - dmin);
+  return x >= 1 ? dmax : (x <= 0 ? dmin : imp);
 }
 
 // Per-lane state: the root part is the same in both lanes of a pair.
@@ -344,16 +358,18 @@ HCP_FN void pair_substep(const Ctx& c, const HcModel& cm, const LegModel& L, Pai
     const bool lo = dlo < 0, hi = !lo && dhi < 0;
     if (lo || hi) {
       const double sign = lo ? 1.0 : -1.0, dist = lo ? dlo : dhi;
-      double imp, K, B;
-      pair_impedance(cm.solref_limit, cm.solimp_limit, dist, imp, K, B);
-      const double Rr = fmax(MINVAL, (1 - imp) * L.dof_invw[j] / imp);
-      RowP q = rowp(c, n++);
-      HCP_RF(q, F_JR + 0) = 0; HCP_RF(q, F_JR + 1) = 0; HCP_RF(q, F_JR + 2) = 0;
-      HCP_RF(q, F_JL + 0) = j == 0 ? sign : 0.0;
-      HCP_RF(q, F_JL + 1) = j == 1 ? sign : 0.0;
-      HCP_RF(q, F_JL + 2) = j == 2 ? sign : 0.0;
-      HCP_RF(q, F_D) = 1 / Rr;
-      HCP_RF(q, F_AREF) = -B * (sign * s.vl[j]) - K * imp * dist;
+      const double imp = pair_imp(cm, 1, dist);
+      // D = 1 / R, R = max(MINVAL, (1 - imp) * diagApprox / imp): one division
+      const double D = imp / fmax(MINVAL * imp, (1 - imp) * L.dof_invw[j]);
+      const double aref = -cm.imp_B[1] * (sign * s.vl[j]) - cm.imp_K[1] * imp * dist;
+      with_row(c, n++, [&](auto q) {
+        q[F_JR + 0] = 0; q[F_JR + 1] = 0; q[F_JR + 2] = 0;
+        q[F_JL + 0] = j == 0 ? sign : 0.0;
+        q[F_JL + 1] = j == 1 ? sign : 0.0;
+        q[F_JL + 2] = j == 2 ? sign : 0.0;
+        q[F_D] = D;
+        q[F_AREF] = aref;
+      });
     }
   }
 #pragma unroll 1
@@ -385,26 +401,27 @@ HCP_FN void pair_substep(const Ctx& c, const HcModel& cm, const LegModel& L, Pai
       }
       const double velx = s.vr[0] + jx2 * s.vr[2] + lx[0] * s.vl[0] + lx[1] * s.vl[1] + lx[2] * s.vl[2];
       const double velz = s.vr[1] + jz2 * s.vr[2] + lz[0] * s.vl[0] + lz[1] * s.vl[1] + lz[2] * s.vl[2];
-      double imp, K, B;
-      pair_impedance(cm.solref, cm.solimp, dist, imp, K, B);
+      const double imp = pair_imp(cm, 0, dist);
       const double tran = L.invw_tran[g];
       const double dA = tran + cm.mu * cm.mu * tran;
-      const double Rr = fmax(MINVAL, (1 - imp) * dA / imp) * (2 * cm.mu * cm.mu);
-      const double D = 1 / Rr, kip = K * imp * dist;
+      // D = 1 / R, R = max(MINVAL, (1 - imp) * dA / imp) * 2 mu^2: one division
+      const double D = imp / (fmax(MINVAL * imp, (1 - imp) * dA) * (2 * cm.mu * cm.mu));
+      const double B = cm.imp_B[0], kip = cm.imp_K[0] * imp * dist;
       // pyramid edges n + mu t, n - mu t; the two edges along +-y coincide with n in the
       // plane and are merged into one row of weight 2 D
 #pragma unroll
       for (int e = 0; e < 3; ++e) {
         const double sm = e == 0 ? cm.mu : (e == 1 ? -cm.mu : 0.0);
-        RowP q = rowp(c, n + e);
-        HCP_RF(q, F_JR + 0) = sm;            // jz[0] + sm * jx[0] = 0 + sm * 1
-        HCP_RF(q, F_JR + 1) = 1.0;           // jz[1] + sm * jx[1] = 1 + sm * 0
-        HCP_RF(q, F_JR + 2) = jz2 + sm * jx2;
-        HCP_RF(q, F_JL + 0) = lz[0] + sm * lx[0];
-        HCP_RF(q, F_JL + 1) = lz[1] + sm * lx[1];
-        HCP_RF(q, F_JL + 2) = lz[2] + sm * lx[2];
-        HCP_RF(q, F_D) = e == 2 ? 2 * D : D;
-        HCP_RF(q, F_AREF) = -B * (velz + sm * velx) - kip;
+        with_row(c, n + e, [&](auto q) {
+          q[F_JR + 0] = sm;   // jz[0] + sm * jx[0] = 0 + sm * 1
+          q[F_JR + 1] = 1.0;  // jz[1] + sm * jx[1] = 1 + sm * 0
+          q[F_JR + 2] = jz2 + sm * jx2;
+          q[F_JL + 0] = lz[0] + sm * lx[0];
+          q[F_JL + 1] = lz[1] + sm * lx[1];
+          q[F_JL + 2] = lz[2] + sm * lx[2];
+          q[F_D] = e == 2 ? 2 * D : D;
+          q[F_AREF] = -B * (velz + sm * velx) - kip;
+        });
       }
       n += 3;
     }
@@ -419,14 +436,13 @@ HCP_FN void pair_substep(const Ctx& c, const HcModel& cm, const LegModel& L, Pai
     double Mar[3], Mal[3], gr[3], gl[3], sr[3], sl[3], Mvr[3], Mvl[3];
     {  // warmstart: the better of qacc_warmstart and qacc_smooth
       double cw = 0, cs = 0;
-      for (int r = 0; r < n; ++r) {
-        RowP q = rowp(c, r);
-        const double aref = HCP_RF(q, F_AREF), D = HCP_RF(q, F_D);
+      for_rows(c, n, [&](auto q) {
+        const double aref = q[F_AREF], D = q[F_D];
         const double sw = row_dot(q, s.wr, s.wl) - aref;
         const double ss = row_dot(q, asr, asl) - aref;
         if (sw < 0) cw += 0.5 * D * sw * sw;
         if (ss < 0) cs += 0.5 * D * ss * ss;
-      }
+      });
       pair_mv(c, M, s.wr, s.wl, Mar, Mal);
 #pragma unroll
       for (int i = 0; i < 3; ++i) cw += 0.5 * (Mal[i] - fsl[i]) * (s.wl[i] - asl[i]);
@@ -450,15 +466,16 @@ HCP_FN void pair_substep(const Ctx& c, const HcModel& cm, const LegModel& L, Pai
       double fo[3] = {0, 0, 0}, ho[6] = {0, 0, 0, 0, 0, 0}, co = 0;
 #pragma unroll
       for (int i = 0; i < 3; ++i) fcl[i] = 0;
-      for (int r = 0; r < n; ++r) {
-        RowP q = rowp(c, r);
-        const double sj = row_dot(q, ar, al) - HCP_RF(q, F_AREF);
-        HCP_RF(q, F_JAR) = sj;
+      for_rows(c, n, [&](auto q) {
+        const double j0 = q[F_JR + 0], j1 = q[F_JR + 1], j2 = q[F_JR + 2];
+        const double l0 = q[F_JL + 0], l1 = q[F_JL + 1], l2 = q[F_JL + 2];
+        const double D = q[F_D];
+        const double sj = j0 * ar[0] + j1 * ar[1] + j2 * ar[2] + l0 * al[0] + l1 * al[1] +
+                          l2 * al[2] - q[F_AREF];
+        q[F_JAR] = sj;
         if (sj < 0) {
-          const double D = HCP_RF(q, F_D), f = -D * sj;
+          const double f = -D * sj;
           co += 0.5 * D * sj * sj;
-          const double j0 = HCP_RF(q, F_JR + 0), j1 = HCP_RF(q, F_JR + 1), j2 = HCP_RF(q, F_JR + 2);
-          const double l0 = HCP_RF(q, F_JL + 0), l1 = HCP_RF(q, F_JL + 1), l2 = HCP_RF(q, F_JL + 2);
           fo[0] += j0 * f; fo[1] += j1 * f; fo[2] += j2 * f;
           ho[0] += D * j0 * j0; ho[1] += D * j1 * j0; ho[2] += D * j1 * j1;
           ho[3] += D * j2 * j0; ho[4] += D * j2 * j1; ho[5] += D * j2 * j2;
@@ -469,7 +486,7 @@ HCP_FN void pair_substep(const Ctx& c, const HcModel& cm, const LegModel& L, Pai
           H.C[1][0] += D * l1 * j0; H.C[1][1] += D * l1 * j1; H.C[1][2] += D * l1 * j2;
           H.C[2][0] += D * l2 * j0; H.C[2][1] += D * l2 * j1; H.C[2][2] += D * l2 * j2;
         }
-      }
+      });
       double g2o = 0;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -519,26 +536,21 @@ HCP_FN void pair_substep(const Ctx& c, const HcModel& cm, const LegModel& L, Pai
       q1 += psum(c, q1o);
       q2 += psum(c, q2o);
       sn2 += psum(c, sno);
-      for (int r = 0; r < n; ++r) {
-        RowP q = rowp(c, r);
-        HCP_RF(q, F_JV) = row_dot(q, sr, sl);
-      }
+      for_rows(c, n, [&](auto q) { q[F_JV] = row_dot(q, sr, sl); });
       // stop at |phi'(alpha)| < tolerance * ls_tolerance * |search| / scale (MuJoCo's scaled
       // gradient tolerance of the 1-D problem, ls_tolerance = 0.01)
       const double gtol = cm.tolerance * 0.01 * sqrt(sn2) / scale;
       double lo = 0, hi = INFINITY, alpha = 0;
       for (int k = 0; k < cm.ls_iter; ++k) {
         double d1o = 0, d2o = 0;
-        for (int r = 0; r < n; ++r) {
-          RowP q = rowp(c, r);
-          const double jv = HCP_RF(q, F_JV);
-          const double x = HCP_RF(q, F_JAR) + alpha * jv;
+        for_rows(c, n, [&](auto q) {
+          const double jv = q[F_JV], D = q[F_D];
+          const double x = q[F_JAR] + alpha * jv;
           if (x < 0) {
-            const double D = HCP_RF(q, F_D);
             d1o += D * x * jv;
             d2o += D * jv * jv;
           }
-        }
+        });
         const double d1 = (q1 + alpha * q2) + psum(c, d1o);
         const double d2 = q2 + psum(c, d2o);
         if (fabs(d1) < gtol) break;

@@ -54,7 +54,7 @@ extern "C" int hc_pair_host_step(const void* model_blob, double* q, double* v, d
     double srow[hcp::MAXR * hcp::NF], ovf[hcp::MAXR * hcp::NF];
     hcp::Ctx c;
     c.side = side; c.pm = 0; c.chan = &chan;
-    c.srow = srow; c.sstride = 1; c.ks = ks; c.ovf = ovf;
+    c.srow = srow; c.ks = ks; c.ovf = ovf;
     for (int k = 0; k < nsub; ++k) hcp::pair_substep(c, cm, lm[side], s);
   };
   std::thread t1(lane, 1);
