@@ -854,10 +854,12 @@ __device__ LegModel g_leg_model[2];
 // constraint rows of every lane, interleaved by thread.
 //
 // kMinBlocks = resident CTAs per SM the register allocation must allow: 4 (<= 255 registers, no
-// spills) while 8 warps per SM cover the batch, 8 (<= 128 registers) for batches that need
-// more warps in flight than that to stay in one wave.
+// spills) is the default at every batch size; 7 (<= 144 registers: 32768 envs in ONE wave of 14
+// warps per SM instead of 1.7 waves of 8) is kept as a measured alternative
+// (ENVPOOL_B200_HC_PAIR_MINB=7; the 128-register build for 8 CTAs per SM measured 28 % slower
+// than the default at 32768 envs and was dropped).
 template <int kMinBlocks>
-__global__ void __launch_bounds__(kPairBlock, kMinBlocks)
+__global__ void __launch_bounds__(kPairBlock) __maxnreg__(kMinBlocks == 7 ? 144 : 255)
 hc_pair_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict__ action,
                const int32_t* __restrict__ env_ids, int n, int force_reset, int T, int ks) {
   extern __shared__ double srows[];
@@ -1022,7 +1024,7 @@ MjcPool* mjc_pool_create(int num_envs, int precision, int frame_skip, double ctr
     if (cudaMemcpyToSymbol(g_leg_model, legs, sizeof(legs)) != cudaSuccess ||
         cudaFuncSetAttribute(hc_pair_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_max) != cudaSuccess ||
-        cudaFuncSetAttribute(hc_pair_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(hc_pair_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_max) != cudaSuccess) {
       delete m;
       return nullptr;
@@ -1057,11 +1059,10 @@ static int hc_lane_shift(int) {
   return (forced >= 0 && forced <= 5) ? forced : 0;
 }
 
-// Launch shape of the pair kernel for a batch of n rows.  CTAs needed per SM for one wave:
-//   <= 4: the 255-register build; rows per lane in shared memory = everything (27) while one
-//         CTA per SM covers the batch, less as 2-4 CTAs share an SM;
-//   >  4: the 128-register build, 8 CTAs (16 warps) per SM, 5 rows per lane in shared memory.
-// ENVPOOL_B200_HC_PAIR_KS / ENVPOOL_B200_HC_PAIR_MINB (4 | 8) override (A/B switches).
+// Launch shape of the pair kernel for a batch of n rows: rows per lane in shared memory =
+// everything (27) while one CTA per SM covers the batch, less as more CTAs (up to `minb`, what
+// the register allocation of the build allows) share an SM.
+// ENVPOOL_B200_HC_PAIR_KS / ENVPOOL_B200_HC_PAIR_MINB (4 | 7) override (A/B switches).
 struct PairShape {
   int ks, minb;
 };
@@ -1083,8 +1084,7 @@ static PairShape pair_shape(int n) {
   const int ctas = (2 * n + kPairBlock - 1) / kPairBlock;
   const int need = (ctas + sms - 1) / sms;  // CTAs per SM for a single wave
   PairShape sh;
-  sh.minb = need > 4 ? 8 : 4;
-  if (forced_minb == 4 || forced_minb == 8) sh.minb = forced_minb;
+  sh.minb = (forced_minb == 7) ? 7 : 4;
   int per_sm = need < 1 ? 1 : (need > sh.minb ? sh.minb : need);
   const int row_bytes = hcp::NF * kPairBlock * (int)sizeof(double);
   int ks = (int)((216 * 1024 / per_sm) / row_bytes);
@@ -1100,8 +1100,8 @@ static void launch_pair(MjcPool* m, const StateView& sv, const OutView& ov, cons
   const PairShape sh = pair_shape(n);
   const int grid = (int)((2 * (int64_t)n + kPairBlock - 1) / kPairBlock);
   const size_t smem = (size_t)sh.ks * hcp::NF * kPairBlock * sizeof(double);
-  if (sh.minb == 8)
-    hc_pair_kernel<8><<<grid, kPairBlock, smem, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
+  if (sh.minb == 7)
+    hc_pair_kernel<7><<<grid, kPairBlock, smem, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
                                                           force_reset, T, sh.ks);
   else
     hc_pair_kernel<4><<<grid, kPairBlock, smem, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
