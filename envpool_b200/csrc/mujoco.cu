@@ -841,7 +841,7 @@ namespace epb {
 namespace {
 
 constexpr int kPairBlock = 64;  // threads per CTA = 32 envs
-constexpr int kPairKsMin = 5;   // fewest constraint rows per lane ever held in shared memory
+constexpr int kPairKsMin = 9;   // fewest constraint rows per lane ever held in shared memory
 static_assert(kPairBlock == HCP_SSTRIDE, "row interleave stride = threads per CTA");
 
 // the two LegModel tables in global memory (written once per process, mjc_pool_create): every
@@ -853,13 +853,10 @@ __device__ LegModel g_leg_model[2];
 // common columns), lane 2*row + 1 the front leg.  Dynamic shared memory: the first `ks`
 // constraint rows of every lane, interleaved by thread.
 //
-// kMinBlocks = resident CTAs per SM the register allocation must allow: 4 (<= 255 registers, no
-// spills) is the default at every batch size; 7 (<= 144 registers: 32768 envs in ONE wave of 14
-// warps per SM instead of 1.7 waves of 8) is kept as a measured alternative
-// (ENVPOOL_B200_HC_PAIR_MINB=7; the 128-register build for 8 CTAs per SM measured 28 % slower
-// than the default at 32768 envs and was dropped).
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kPairBlock) __maxnreg__(kMinBlocks == 7 ? 144 : 255)
+// 245 registers, no spills: 4 CTAs (8 warps) per SM.  Builds capped at 144 and 128 registers
+// (7 / 8 CTAs per SM: 32768 envs in ONE wave instead of 1.7) were measured and dropped: 400 and
+// 357 us per step at 32768 envs against 278 -- their spills cost more than the second wave.
+__global__ void __launch_bounds__(kPairBlock)
 hc_pair_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict__ action,
                const int32_t* __restrict__ env_ids, int n, int force_reset, int T, int ks) {
   extern __shared__ double srows[];
@@ -1022,9 +1019,7 @@ MjcPool* mjc_pool_create(int num_envs, int precision, int frame_skip, double ctr
     hcm::leg_model_of(host_model, 1, &legs[1]);
     const int smem_max = hcp::MAXR * hcp::NF * kPairBlock * (int)sizeof(double);
     if (cudaMemcpyToSymbol(g_leg_model, legs, sizeof(legs)) != cudaSuccess ||
-        cudaFuncSetAttribute(hc_pair_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem_max) != cudaSuccess ||
-        cudaFuncSetAttribute(hc_pair_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(hc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_max) != cudaSuccess) {
       delete m;
       return nullptr;
@@ -1059,22 +1054,15 @@ static int hc_lane_shift(int) {
   return (forced >= 0 && forced <= 5) ? forced : 0;
 }
 
-// Launch shape of the pair kernel for a batch of n rows: rows per lane in shared memory =
-// everything (27) while one CTA per SM covers the batch, less as more CTAs (up to `minb`, what
-// the register allocation of the build allows) share an SM.
-// ENVPOOL_B200_HC_PAIR_KS / ENVPOOL_B200_HC_PAIR_MINB (4 | 7) override (A/B switches).
-struct PairShape {
-  int ks, minb;
-};
-static PairShape pair_shape(int n) {
-  static const int forced_ks = [] {
+// Rows per lane kept in shared memory: everything (27) while one CTA per SM covers the batch,
+// less as more CTAs share an SM (at most 4: what the kernel's registers allow).
+// ENVPOOL_B200_HC_PAIR_KS overrides (A/B switch).
+static int pair_rows_in_smem(int n) {
+  static const int forced = [] {
     const char* e = getenv("ENVPOOL_B200_HC_PAIR_KS");
     return e ? atoi(e) : 0;
   }();
-  static const int forced_minb = [] {
-    const char* e = getenv("ENVPOOL_B200_HC_PAIR_MINB");
-    return e ? atoi(e) : 0;
-  }();
+  if (forced >= kPairKsMin && forced <= hcp::MAXR) return forced;
   static const int sms = [] {
     int dev = 0, v = 148;
     cudaGetDevice(&dev);
@@ -1082,30 +1070,22 @@ static PairShape pair_shape(int n) {
     return v > 0 ? v : 148;
   }();
   const int ctas = (2 * n + kPairBlock - 1) / kPairBlock;
-  const int need = (ctas + sms - 1) / sms;  // CTAs per SM for a single wave
-  PairShape sh;
-  sh.minb = (forced_minb == 7) ? 7 : 4;
-  int per_sm = need < 1 ? 1 : (need > sh.minb ? sh.minb : need);
+  int per_sm = (ctas + sms - 1) / sms;  // CTAs per SM for a single wave
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
   const int row_bytes = hcp::NF * kPairBlock * (int)sizeof(double);
   int ks = (int)((216 * 1024 / per_sm) / row_bytes);
   ks = ks > hcp::MAXR ? hcp::MAXR : ks;
-  sh.ks = ks < kPairKsMin ? kPairKsMin : ks;
-  if (forced_ks >= kPairKsMin && forced_ks <= hcp::MAXR) sh.ks = forced_ks;
-  return sh;
+  return ks < kPairKsMin ? kPairKsMin : ks;
 }
 
 static void launch_pair(MjcPool* m, const StateView& sv, const OutView& ov, const double* d_action,
                         const int32_t* d_env_ids, int n, int force_reset, int T,
                         cudaStream_t stream) {
-  const PairShape sh = pair_shape(n);
+  const int ks = pair_rows_in_smem(n);
   const int grid = (int)((2 * (int64_t)n + kPairBlock - 1) / kPairBlock);
-  const size_t smem = (size_t)sh.ks * hcp::NF * kPairBlock * sizeof(double);
-  if (sh.minb == 7)
-    hc_pair_kernel<7><<<grid, kPairBlock, smem, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
-                                                          force_reset, T, sh.ks);
-  else
-    hc_pair_kernel<4><<<grid, kPairBlock, smem, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
-                                                          force_reset, T, sh.ks);
+  const size_t smem = (size_t)ks * hcp::NF * kPairBlock * sizeof(double);
+  hc_pair_kernel<<<grid, kPairBlock, smem, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
+                                                     force_reset, T, ks);
 }
 
 cudaError_t mjc_launch_step(MjcPool* m, const StateView& sv, const OutView& ov,
