@@ -172,6 +172,7 @@ struct epb_pool {
   bool x_attached = false;
   long long x_timeout_ns = 10000000000LL;
   bool x_fused = false;  // peer stores issued by the step kernel's epilogue (else push_kernel)
+  bool x_side_push = true;  // captured chains: push_kernel on the side branch, not in the chain
   uint64_t x_steps = 0;   // host count of exchanged steps; step t uses slot t % D
   uint64_t x_waited = 0;  // host count of enqueued waits
   cudaStream_t x_side = nullptr;            // wait branch of the engine-captured chains
@@ -1088,7 +1089,8 @@ int epb_rollout_device(epb_pool* p, const void* d_actions, int T, void* const* d
 namespace {
 
 int exchange_step(epb_pool* p, const void* d_action, cudaStream_t s, int chain_k,
-                  const void* next_action);
+                  const void* next_action, cudaStream_t push_stream = nullptr,
+                  cudaEvent_t step_done = nullptr);
 int exchange_wait_launch(epb_pool* p, cudaStream_t s);
 
 // K consecutive sync steps on `st`, step k reading action row (t0 + k) % T.  `fork` (only
@@ -1144,15 +1146,28 @@ int run_chain(epb_pool* p, cudaStream_t st, const ChainKey& c, bool fork, cudaEv
     if (c.exchange) {
       if (xfork && k >= D - 1)
         EPB_CUDA(cudaStreamWaitEvent(st, p->x_ev_wait[(k - (D - 1)) % D], 0));
-      rc = exchange_step(p, a, st, rec ? -2 : -1, nx);
-      if (rc != EPB_OK) return rc;
-      if (xfork) {
+      if (xfork && p->x_side_push) {
+        // the peer stores leave the step chain: step k only computes (into its local slot); a
+        // copy kernel on the side branch pushes the wire columns and the wait for the peers'
+        // step k follows it there.  The chain then advances at the step-only rate while the
+        // NVLink traffic, its system fences and the flag round trips ride beside it (a kernel
+        // that stores to a peer cannot complete before those stores have drained).
+        rc = exchange_step(p, a, st, rec ? -2 : -1, nx, p->x_side, p->x_ev_step[k % D]);
+        if (rc != EPB_OK) return rc;
+        rc = exchange_wait_launch(p, p->x_side);
+        if (rc != EPB_OK) return rc;
+        EPB_CUDA(cudaEventRecord(p->x_ev_wait[k % D], p->x_side));
+      } else if (xfork) {
+        rc = exchange_step(p, a, st, rec ? -2 : -1, nx);
+        if (rc != EPB_OK) return rc;
         EPB_CUDA(cudaEventRecord(p->x_ev_step[k % D], st));
         EPB_CUDA(cudaStreamWaitEvent(p->x_side, p->x_ev_step[k % D], 0));
         rc = exchange_wait_launch(p, p->x_side);
         if (rc != EPB_OK) return rc;
         EPB_CUDA(cudaEventRecord(p->x_ev_wait[k % D], p->x_side));
       } else {
+        rc = exchange_step(p, a, st, rec ? -2 : -1, nx);
+        if (rc != EPB_OK) return rc;
         rc = exchange_wait_launch(p, st);
         if (rc != EPB_OK) return rc;
       }
@@ -1323,6 +1338,10 @@ int epb_exchange_init(epb_pool* p, int world, int rank, void* ipc_handle_out) {
   // HalfCheetah's kernels have no forwarding epilogue; ENVPOOL_B200_EXCHANGE=push is the A/B switch
   const char* mode = getenv("ENVPOOL_B200_EXCHANGE");
   p->x_fused = p->kind != EPB_HALF_CHEETAH && !(mode && strcmp(mode, "push") == 0);
+  // engine-captured chains: push on the side branch (default) or inside the step chain
+  // (ENVPOOL_B200_EXCHANGE_CHAIN=inline: the fused epilogue / the push kernel behind the step)
+  const char* cmode = getenv("ENVPOOL_B200_EXCHANGE_CHAIN");
+  p->x_side_push = !(cmode && strcmp(cmode, "inline") == 0);
   if (const char* to = getenv("ENVPOOL_B200_EXCHANGE_TIMEOUT_S")) {
     double sec = atof(to);
     if (sec > 0) p->x_timeout_ns = (long long)(sec * 1e9);
@@ -1381,7 +1400,7 @@ namespace {
 // One exchanged step on `s`: the step kernel writes slot[t % D][rank] of the local allocation,
 // checks the credit (slot t % D released everywhere), forwards its wire columns, publishes.
 int exchange_step(epb_pool* p, const void* d_action, cudaStream_t s, int chain_k,
-                  const void* next_action) {
+                  const void* next_action, cudaStream_t push_stream, cudaEvent_t step_done) {
   const int D = p->x_depth;
   const uint64_t t = p->x_steps;
   // the credit of step t needs this rank's own release of step t - D, which its wait for
@@ -1394,7 +1413,7 @@ int exchange_step(epb_pool* p, const void* d_action, cudaStream_t s, int chain_k
   char* mine = p->x_base + p->x_mine(slot);
   int32_t* wire = reinterpret_cast<int32_t*>(mine + p->slab_bytes);
   const int force = d_action ? 0 : 1;
-  if (p->x_fused) {
+  if (p->x_fused && !push_stream) {
     int rc = launch_batch(p, d_action, nullptr, p->N, force, mine, s, p->x_view(slot), chain_k,
                           wire, next_action);
     if (rc != EPB_OK) return rc;
@@ -1402,6 +1421,11 @@ int exchange_step(epb_pool* p, const void* d_action, cudaStream_t s, int chain_k
     int rc = launch_batch(p, d_action, nullptr, p->N, force, mine, s, nullptr, chain_k, wire,
                           next_action);
     if (rc != EPB_OK) return rc;
+    if (push_stream) {  // the copy kernel goes on the caller's side branch, behind this step
+      EPB_CUDA(cudaEventRecord(step_done, s));
+      EPB_CUDA(cudaStreamWaitEvent(push_stream, step_done, 0));
+      s = push_stream;
+    }
     int64_t n16 = 0;
     for (size_t k = 8; k < p->keys.size(); ++k)
       n16 += ((int64_t)p->N * p->keys[k].row_bytes + 15) / 16;

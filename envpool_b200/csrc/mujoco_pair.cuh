@@ -460,6 +460,9 @@ HCP_FN void pair_substep(const Ctx& c, const HcModel& cm, const LegModel& L, Pai
     }
     const double scale = 1.0 / (cm.meaninertia * hcm::NV);
     double cost = 0;
+#if defined(HCP_STATS)
+    int st_newton = 0;
+#endif
     for (int iter = 0; iter <= cm.max_iter; ++iter) {
       pair_mv(c, M, ar, al, Mar, Mal);
       Arrow H = M;
@@ -523,48 +526,89 @@ HCP_FN void pair_substep(const Ctx& c, const HcModel& cm, const LegModel& L, Pai
 #pragma unroll
       for (int i = 0; i < 3; ++i) { sr[i] = -sr[i]; sl[i] = -sl[i]; }
       pair_mv(c, M, sr, sl, Mvr, Mvl);
-      double q1 = 0, q2 = 0, sn2 = 0, q1o = 0, q2o = 0, sno = 0;
+      double q1 = 0, q2 = 0, sn2 = 0, gs = 0, q1o = 0, q2o = 0, sno = 0, gso = 0;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         q1 += sr[i] * (Mar[i] - fsr[i]);
         q2 += sr[i] * Mvr[i];
         sn2 += sr[i] * sr[i];
+        gs += sr[i] * gr[i];
         q1o += sl[i] * (Mal[i] - fsl[i]);
         q2o += sl[i] * Mvl[i];
         sno += sl[i] * sl[i];
+        gso += sl[i] * gl[i];
       }
       q1 += psum(c, q1o);
       q2 += psum(c, q2o);
       sn2 += psum(c, sno);
-      for_rows(c, n, [&](auto q) { q[F_JV] = row_dot(q, sr, sl); });
-      // stop at |phi'(alpha)| < tolerance * ls_tolerance * |search| / scale (MuJoCo's scaled
-      // gradient tolerance of the 1-D problem, ls_tolerance = 0.01)
+      gs += psum(c, gso);
+      // Exact line search on phi(alpha) = cost(a + alpha * search), by safeguarded Newton steps on
+      // phi'; stop at |phi'(alpha)| < tolerance * ls_tolerance * |search| / scale (MuJoCo's scaled
+      // gradient tolerance of the 1-D problem, ls_tolerance = 0.01).
+      // The evaluation at alpha = 0 needs no pass over the rows: phi'(0) = grad . search, and
+      // because search = -H^-1 grad with H built from exactly the rows active at alpha = 0,
+      // phi''(0) = search . H search = -phi'(0): the first Newton step lands on alpha = 1.  So
+      // the first row pass evaluates alpha = 1 -- fused with the pass that computes J search --
+      // and in two of three line searches (profiles/r2_summary.md) it is also the last.
       const double gtol = cm.tolerance * 0.01 * sqrt(sn2) / scale;
-      double lo = 0, hi = INFINITY, alpha = 0;
-      for (int k = 0; k < cm.ls_iter; ++k) {
+      double alpha = 0;
+#if defined(HCP_STATS)
+      int st_ls = 0;
+#endif
+      if (gs < 0 && !(fabs(gs) < gtol)) {
+        double lo = 0, hi = INFINITY;
+        alpha = 1.0;
         double d1o = 0, d2o = 0;
         for_rows(c, n, [&](auto q) {
-          const double jv = q[F_JV], D = q[F_D];
-          const double x = q[F_JAR] + alpha * jv;
+          const double jv = row_dot(q, sr, sl), D = q[F_D];
+          q[F_JV] = jv;
+          const double x = q[F_JAR] + jv;
           if (x < 0) {
             d1o += D * x * jv;
             d2o += D * jv * jv;
           }
         });
-        const double d1 = (q1 + alpha * q2) + psum(c, d1o);
-        const double d2 = q2 + psum(c, d2o);
-        if (fabs(d1) < gtol) break;
-        if (d1 < 0) lo = alpha; else hi = alpha;
-        double next = alpha - d1 / d2;
-        if (!(next > lo && next < hi)) next = (hi == INFINITY) ? 2 * alpha + 1 : 0.5 * (lo + hi);
-        if (next == alpha) break;
-        alpha = next;
+        for (int k = 1; k < cm.ls_iter; ++k) {
+#if defined(HCP_STATS)
+          ++st_ls;
+#endif
+          if (k > 1) {
+            d1o = 0;
+            d2o = 0;
+            for_rows(c, n, [&](auto q) {
+              const double jv = q[F_JV], D = q[F_D];
+              const double x = q[F_JAR] + alpha * jv;
+              if (x < 0) {
+                d1o += D * x * jv;
+                d2o += D * jv * jv;
+              }
+            });
+          }
+          const double d1 = (q1 + alpha * q2) + psum(c, d1o);
+          const double d2 = q2 + psum(c, d2o);
+          if (fabs(d1) < gtol) break;
+          if (d1 < 0) lo = alpha; else hi = alpha;
+          double next = alpha - d1 / d2;
+          if (!(next > lo && next < hi)) next = (hi == INFINITY) ? 2 * alpha + 1 : 0.5 * (lo + hi);
+          if (next == alpha) break;
+          alpha = next;
+        }
       }
+#if defined(HCP_STATS)
+      ++st_newton;
+      if (c.side == 0) ++g_ls_hist[st_ls < 63 ? st_ls : 63];
+#endif
       if (alpha == 0) break;
 #pragma unroll
       for (int i = 0; i < 3; ++i) { ar[i] += alpha * sr[i]; al[i] += alpha * sl[i]; }
     }
+#if defined(HCP_STATS)
+    if (c.side == 0) ++g_newton_hist[st_newton < 31 ? st_newton : 31];
+#endif
   }
+#if defined(HCP_STATS)
+  if (c.side == 0) ++g_rows_hist[(int)ntot < 31 ? (int)ntot : 31];
+#endif
   // ---- mj_Euler with implicit joint damping -------------------------------------------------------
   {
     Arrow E = M;
