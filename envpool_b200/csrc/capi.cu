@@ -176,7 +176,8 @@ struct epb_pool {
   uint64_t x_steps = 0;   // host count of exchanged steps; step t uses slot t % D
   uint64_t x_waited = 0;  // host count of enqueued waits
   cudaStream_t x_side = nullptr;            // wait branch of the engine-captured chains
-  cudaEvent_t x_ev_step[kMaxDepth] = {}, x_ev_wait[kMaxDepth] = {};
+  cudaStream_t x_push = nullptr;            // push branch (x_side_push)
+  cudaEvent_t x_ev_step[kMaxDepth] = {}, x_ev_wait[kMaxDepth] = {}, x_ev_push[kMaxDepth] = {};
 
   int64_t x_mine(int slot) const { return ((int64_t)slot * x_world + x_rank) * x_slice; }
   ExchangeCtl* x_ctl() const { return reinterpret_cast<ExchangeCtl*>(x_base + x_ctl_off); }
@@ -729,12 +730,14 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->mark_side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->x_side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->x_push, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_mark, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&p->ev_t0);
   if (e == cudaSuccess) e = cudaEventCreate(&p->ev_t1);
   for (int h = 0; h < kMaxDepth && e == cudaSuccess; ++h) {
     e = cudaEventCreateWithFlags(&p->x_ev_step[h], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->x_ev_wait[h], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->x_ev_push[h], cudaEventDisableTiming);
   }
   for (int h = 0; h < 2 && e == cudaSuccess; ++h) {
     e = cudaEventCreateWithFlags(&p->ev_step[h], cudaEventDisableTiming);
@@ -850,7 +853,7 @@ int epb_destroy(epb_pool* p) {
   if (p->d_slab) cudaFree(p->d_slab);
   if (p->d_action) cudaFree(p->d_action);
   if (p->d_ids) cudaFree(p->d_ids);
-  for (cudaStream_t* st : {&p->side, &p->mark_side, &p->x_side}) {
+  for (cudaStream_t* st : {&p->side, &p->mark_side, &p->x_side, &p->x_push}) {
     if (*st) {
       cudaStreamSynchronize(*st);
       cudaStreamDestroy(*st);
@@ -861,6 +864,7 @@ int epb_destroy(epb_pool* p) {
   for (int h = 0; h < kMaxDepth; ++h) {
     if (p->x_ev_step[h]) cudaEventDestroy(p->x_ev_step[h]);
     if (p->x_ev_wait[h]) cudaEventDestroy(p->x_ev_wait[h]);
+    if (p->x_ev_push[h]) cudaEventDestroy(p->x_ev_push[h]);
   }
   for (int h = 0; h < 2; ++h) {
     if (p->ev_step[h]) cudaEventDestroy(p->ev_step[h]);
@@ -1147,13 +1151,21 @@ int run_chain(epb_pool* p, cudaStream_t st, const ChainKey& c, bool fork, cudaEv
       if (xfork && k >= D - 1)
         EPB_CUDA(cudaStreamWaitEvent(st, p->x_ev_wait[(k - (D - 1)) % D], 0));
       if (xfork && p->x_side_push) {
-        // the peer stores leave the step chain: step k only computes (into its local slot); a
-        // copy kernel on the side branch pushes the wire columns and the wait for the peers'
-        // step k follows it there.  The chain then advances at the step-only rate while the
-        // NVLink traffic, its system fences and the flag round trips ride beside it (a kernel
-        // that stores to a peer cannot complete before those stores have drained).
-        rc = exchange_step(p, a, st, rec ? -2 : -1, nx, p->x_side, p->x_ev_step[k % D]);
+        // The peer stores leave the step chain: step k only computes (into its local slot
+        // k % D); push(k), a copy kernel on a branch of its own, sends the wire columns, and
+        // wait_derive(k) follows push(k) on a third branch.  Three pipelines beside each other:
+        //   steps     step(k) after step(k-1), wait_derive(k-D+1) (run-ahead bound) and
+        //             push(k-D) (the slot it overwrites has been sent)
+        //   pushes    push(k) after step(k) and push(k-1)
+        //   waits     wait_derive(k) after push(k) and wait_derive(k-1)
+        // so the chain advances at max(step, push, wait) per step instead of their sum -- a
+        // kernel that stores to a peer cannot complete before those stores have drained, which
+        // is why the fused epilogue, ideal for ONE step, is the wrong shape for a chain.
+        if (k >= D) EPB_CUDA(cudaStreamWaitEvent(st, p->x_ev_push[(k - D) % D], 0));
+        rc = exchange_step(p, a, st, rec ? -2 : -1, nx, p->x_push, p->x_ev_step[k % D]);
         if (rc != EPB_OK) return rc;
+        EPB_CUDA(cudaEventRecord(p->x_ev_push[k % D], p->x_push));
+        EPB_CUDA(cudaStreamWaitEvent(p->x_side, p->x_ev_push[k % D], 0));
         rc = exchange_wait_launch(p, p->x_side);
         if (rc != EPB_OK) return rc;
         EPB_CUDA(cudaEventRecord(p->x_ev_wait[k % D], p->x_side));

@@ -858,8 +858,7 @@ __device__ LegModel g_leg_model[2];
 // 357 us per step at 32768 envs against 278 -- their spills cost more than the second wave.
 __global__ void __launch_bounds__(kPairBlock)
 hc_pair_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict__ action,
-               const int32_t* __restrict__ env_ids, int n, int force_reset, int T, int ks,
-               int spread) {
+               const int32_t* __restrict__ env_ids, int n, int force_reset, int T, int ks) {
   extern __shared__ double srows[];
   __shared__ LegModel lm[2];
   {
@@ -869,13 +868,8 @@ hc_pair_kernel(StateView sv, OutView ov, HcParams prm, const double* __restrict_
       dst[i] = src[i];
   }
   __syncthreads();
-  // `spread` (default 0): only every (1 << spread)-th lane pair carries an env.  A warp waits
-  // for the slowest of its envs in the constraint solve; small batches leave most of the GPU
-  // idle anyway, so fewer envs per warp cost nothing and shorten that wait.
   const int tid = blockIdx.x * kPairBlock + threadIdx.x;
-  const int pair = tid >> 1, side = tid & 1;
-  if (pair & ((1 << spread) - 1)) return;
-  const int row = pair >> spread;
+  const int row = tid >> 1, side = tid & 1;
   if (row >= n) return;  // both lanes of a pair leave together
   const int eid = env_ids ? env_ids[row] : row;
   const int64_t N = sv.n_envs;
@@ -1087,16 +1081,14 @@ static int pair_rows_in_smem(int n) {
 static void launch_pair(MjcPool* m, const StateView& sv, const OutView& ov, const double* d_action,
                         const int32_t* d_env_ids, int n, int force_reset, int T,
                         cudaStream_t stream) {
-  static const int forced_spread = [] {
-    const char* e = getenv("ENVPOOL_B200_HC_PAIR_SPREAD");
-    return e ? atoi(e) : -1;
-  }();
-  const int spread = (forced_spread >= 0 && forced_spread <= 3) ? forced_spread : 0;
-  const int ks = pair_rows_in_smem(n << spread);
-  const int grid = (int)(((2 * (int64_t)n << spread) + kPairBlock - 1) / kPairBlock);
+  // (Carrying fewer envs per warp -- every 2nd / 4th lane pair idle, so that a warp waits for
+  // the slowest of 8 / 4 envs instead of 16 in the constraint solve -- was measured: 102 / 102 /
+  // 118 us per step at 4096 envs, 110 / 131 / 205 at 8192.  No gain; not kept.)
+  const int ks = pair_rows_in_smem(n);
+  const int grid = (int)((2 * (int64_t)n + kPairBlock - 1) / kPairBlock);
   const size_t smem = (size_t)ks * hcp::NF * kPairBlock * sizeof(double);
   hc_pair_kernel<<<grid, kPairBlock, smem, stream>>>(sv, ov, m->prm, d_action, d_env_ids, n,
-                                                     force_reset, T, ks, spread);
+                                                     force_reset, T, ks);
 }
 
 cudaError_t mjc_launch_step(MjcPool* m, const StateView& sv, const OutView& ov,

@@ -18,5 +18,10 @@ try:
 except Exception as e:
     print('no line', e)
 PY
+ENVPOOL_B200_EXCHANGE_CHAIN=inline timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 20 --warmup 3 --no-configs > $O/bench_inline.txt 2>$O/bench_inline.err
+tail -1 $O/bench_inline.txt | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); wx = d.get('with_exchange') or {}
+print('inline-chain value', round(d['value']/1e9,3), 'G  us/step', round(d['ms_per_step']*1e3,2), 'nvlink in', round(wx.get('nvlink_gbs_in_per_gpu',0),1))" | tee -a $O/summary.txt
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 20 --warmup 3 > $O/bench_ref.txt 2>$O/bench_ref.err
 tail -c 400 $O/bench_ref.txt >> $O/summary.txt
