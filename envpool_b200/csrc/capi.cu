@@ -1473,8 +1473,12 @@ int exchange_wait_launch(epb_pool* p, cudaStream_t s) {
   a.rank = p->x_rank;
   a.depth = p->x_depth;
   a.n = p->N;
+  // CTAs per peer slice: one quad of envs per thread if the GPU has room (2 CTAs per SM over
+  // all peers), never fewer than 16; a 524288-env slice re-expanded by 16 CTAs took 22 us
+  int cap = (2 * 148) / (p->x_world > 1 ? p->x_world - 1 : 1);
+  if (cap < 16) cap = 16;
   int per_peer = (p->N / 4 + 255) / 256;
-  if (per_peer > 16) per_peer = 16;
+  if (per_peer > cap) per_peer = cap;
   if (per_peer < 1) per_peer = 1;
   wait_derive_kernel<<<dim3(per_peer, p->x_world), 256, 0, s>>>(a);
   EPB_CUDA(cudaGetLastError());

@@ -121,14 +121,20 @@ __device__ __forceinline__ void peer_credit(const PeerView* __restrict__ pv) {
   }
 }
 
-// Last-block-done publication: every CTA fences its peer stores at system scope before it
-// counts itself; the CTA that completes the count bumps the sequence number and raises
-// data_flag[rank] on every rank -- ONE system fence, then relaxed flag stores (a release per
-// flag would pay one NVLink round trip per peer).  Call with all threads of the CTA.
+// Last-block-done publication.  Per CTA: barrier (every peer store of the CTA is issued before
+// it), then ONE thread fences at system scope and counts the CTA -- a fence is cumulative: it
+// orders every write that happens-before it, and the barrier puts the whole CTA's stores there
+// (the release pattern of cooperative-groups grid sync and of CUTLASS's semaphore, at .sys
+// scope).  The first version had EVERY thread fence: 2048 warps issuing MEMBAR.SYS behind
+// in-flight NVLink stores was the dominant cost of a small exchange (a 1.5 MB CartPole push took
+// ~14 us, payload time 2 us).  The CTA that completes the count bumps the sequence number,
+// fences once more (acquire side of the ticket, release side of the flags) and raises
+// data_flag[rank] on every rank with relaxed stores (a release per flag would pay one NVLink
+// round trip per peer).  Call with all threads of the CTA.
 __device__ __forceinline__ void peer_publish(const PeerView* __restrict__ pv) {
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     ExchangeCtl* ctl = pv->ctl;
     unsigned int ticket = atomicAdd(&ctl->blocks_done, 1u);
     if (ticket == gridDim.x - 1) {
