@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "epb_exchange_attach_ipc", "epb_step_exchange_device", "epb_exchange_wait",
     "epb_exchange_status", "epb_exchange_slice_bytes", "epb_exchange_depth",
     "epb_step_many_timed", "epb_step_exchange_many_device", "epb_fp64_peak_gflops",
-    "epb_hc_model",
+    "epb_hc_model", "epb_exchange_trace",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -123,6 +123,7 @@ def load_library() -> ctypes.CDLL:
                                       ctypes.POINTER(ctypes.c_float)]
     L.epb_step_exchange_many_device.argtypes = [vp, vp, ci, ci, ci, ci, vp, pp]
     L.epb_fp64_peak_gflops.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+    L.epb_exchange_trace.argtypes = [vp, vp, ctypes.c_int64]
     L.epb_hc_model.restype = ctypes.c_int64
     L.epb_hc_model.argtypes = [vp, ctypes.c_int64]
     _lib = L
@@ -446,6 +447,13 @@ class CPool:
     @property
     def exchange_depth(self) -> int:
         return self.lib.epb_exchange_depth(self.h)
+
+    def exchange_trace(self, steps: int) -> np.ndarray:
+        """[steps, 8] device timestamps (ns) of the exchange kernels; needs
+        ENVPOOL_B200_EXCHANGE_TRACE=1 at exchange_init (include/envpool_b200.h)."""
+        out = np.zeros((steps, 8), dtype=np.int64)
+        _check(self.lib.epb_exchange_trace(self.h, out.ctypes.data, steps))
+        return out
 
     def exchange_status(self):
         steps, bad = ctypes.c_int64(), ctypes.c_int()

@@ -173,10 +173,12 @@ struct epb_pool {
   long long x_timeout_ns = 10000000000LL;
   bool x_fused = false;  // peer stores issued by the step kernel's epilogue (else push_kernel)
   bool x_side_push = true;  // captured chains: push_kernel on the side branch, not in the chain
+  long long* x_trace = nullptr;  // ENVPOOL_B200_EXCHANGE_TRACE: device timeline, 8 stamps / step
+  int64_t x_trace_steps = 0;
   uint64_t x_steps = 0;   // host count of exchanged steps; step t uses slot t % D
   uint64_t x_waited = 0;  // host count of enqueued waits
   cudaStream_t x_side = nullptr;            // wait branch of the engine-captured chains
-  cudaStream_t x_push = nullptr;            // push branch (x_side_push)
+  cudaStream_t x_push[3] = {};              // push branches (x_side_push): push(k) on k % 3
   cudaEvent_t x_ev_step[kMaxDepth] = {}, x_ev_wait[kMaxDepth] = {}, x_ev_push[kMaxDepth] = {};
 
   int64_t x_mine(int slot) const { return ((int64_t)slot * x_world + x_rank) * x_slice; }
@@ -344,8 +346,12 @@ push_kernel(const PeerView* __restrict__ pv, int n) {
   const int world = pv->world, rank = pv->rank;
   const char* __restrict__ src = pv->slice[rank];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    exchange_stamp(pv->ctl, pv->ctl->slot_step[pv->slot], 0);
   peer_credit(pv);
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    exchange_stamp(pv->ctl, pv->ctl->slot_step[pv->slot], 1);
   for (int k = 0; k < pv->ncols; ++k) {
     const int64_t off = pv->col_off[k];
     const int64_t n16 = ((int64_t)n * pv->col_rb[k] + 15) >> 4;
@@ -360,7 +366,7 @@ push_kernel(const PeerView* __restrict__ pv, int n) {
 }
 
 struct WaitArgs {
-  const unsigned long long* data_flag;      // [world] in this rank's allocation
+  const unsigned long long* data_flag;      // [depth][kMaxPeers] in this rank's allocation
   unsigned long long* ack_dst[kMaxPeers];   // &ack_flag[rank] in the allocation of rank g
   char* slots;                              // this rank's slot[0][0]
   int64_t slice, wire_off;
@@ -380,13 +386,15 @@ __global__ void __launch_bounds__(256) wait_derive_kernel(WaitArgs a) {
   ExchangeCtl* ctl = a.ctl;
   const unsigned long long u = ctl->waited;
   const int g = blockIdx.y;
+  if (blockIdx.x == 0 && g == 0 && threadIdx.x == 0) exchange_stamp(ctl, u, 3);
   if (blockIdx.x == 0 && g == 0 && (int)threadIdx.x < a.world)
     st_release_sys(a.ack_dst[threadIdx.x], u);
   if (g != a.rank) {
     if (threadIdx.x == 0) {
       long long t0;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-      while (ld_acquire_sys(a.data_flag + g) < u + 1) {
+      const unsigned long long* flag = a.data_flag + (u % a.depth) * kMaxPeers + g;
+      while (ld_acquire_sys(flag) < u + 1) {
         long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t1 - t0 > a.timeout_ns) {
@@ -395,6 +403,7 @@ __global__ void __launch_bounds__(256) wait_derive_kernel(WaitArgs a) {
         }
         __nanosleep(32);
       }
+      if (blockIdx.x == 0) exchange_stamp(ctl, u, 4, true);
     }
     __syncthreads();
     char* sl = a.slots + ((int64_t)(u % a.depth) * a.world + g) * a.slice;
@@ -431,6 +440,7 @@ __global__ void __launch_bounds__(256) wait_derive_kernel(WaitArgs a) {
   if (threadIdx.x == 0) {
     const unsigned int total = gridDim.x * gridDim.y;
     if (atomicAdd(&ctl->wait_blocks, 1u) == total - 1) {
+      exchange_stamp(ctl, u, 5);
       ctl->wait_blocks = 0;
       ctl->waited = u + 1;
     }
@@ -466,10 +476,11 @@ int upload_views(epb_pool* p) {
     pv.ack = reinterpret_cast<const unsigned long long*>(p->x_base + p->x_ack_off);
     pv.timeout_ns = p->x_timeout_ns;
     pv.depth = p->x_depth;
+    pv.slot = slot;
     for (int g = 0; g < p->x_world; ++g) {
       pv.slice[g] = p->x_peer[g] + p->x_mine(slot);
-      pv.flag[g] =
-          reinterpret_cast<unsigned long long*>(p->x_peer[g] + p->x_data_off) + p->x_rank;
+      pv.flag[g] = reinterpret_cast<unsigned long long*>(p->x_peer[g] + p->x_data_off) +
+                   slot * kMaxPeers + p->x_rank;
     }
     // wire columns: reward, the env keys, the packed common-column word
     int c = 0;
@@ -730,7 +741,8 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->mark_side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->x_side, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->x_push, cudaStreamNonBlocking);
+  for (cudaStream_t& ps : p->x_push)
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_mark, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&p->ev_t0);
   if (e == cudaSuccess) e = cudaEventCreate(&p->ev_t1);
@@ -849,11 +861,13 @@ int epb_destroy(epb_pool* p) {
   for (int g = 0; g < kMaxPeers; ++g)
     if (p->x_ipc[g] && p->x_peer[g]) cudaIpcCloseMemHandle(p->x_peer[g]);
   if (p->x_base) cudaFree(p->x_base);
+  if (p->x_trace) cudaFree(p->x_trace);
   if (p->d_state_blob) cudaFree(p->d_state_blob);
   if (p->d_slab) cudaFree(p->d_slab);
   if (p->d_action) cudaFree(p->d_action);
   if (p->d_ids) cudaFree(p->d_ids);
-  for (cudaStream_t* st : {&p->side, &p->mark_side, &p->x_side, &p->x_push}) {
+  for (cudaStream_t* st : {&p->side, &p->mark_side, &p->x_side, &p->x_push[0], &p->x_push[1],
+                           &p->x_push[2]}) {
     if (*st) {
       cudaStreamSynchronize(*st);
       cudaStreamDestroy(*st);
@@ -1153,18 +1167,23 @@ int run_chain(epb_pool* p, cudaStream_t st, const ChainKey& c, bool fork, cudaEv
       if (xfork && p->x_side_push) {
         // The peer stores leave the step chain: step k only computes (into its local slot
         // k % D); push(k), a copy kernel on a branch of its own, sends the wire columns, and
-        // wait_derive(k) follows push(k) on a third branch.  Three pipelines beside each other:
+        // wait_derive(k) follows on the wait branch.  Pipelines beside each other:
         //   steps     step(k) after step(k-1), wait_derive(k-D+1) (run-ahead bound) and
         //             push(k-D) (the slot it overwrites has been sent)
-        //   pushes    push(k) after step(k) and push(k-1)
+        //   pushes    push(k) after step(k), on push branch k % 3: up to three pushes are in
+        //             flight together (per-slot flags and counters keep them apart)
         //   waits     wait_derive(k) after push(k) and wait_derive(k-1)
-        // so the chain advances at max(step, push, wait) per step instead of their sum -- a
-        // kernel that stores to a peer cannot complete before those stores have drained, which
-        // is why the fused epilogue, ideal for ONE step, is the wrong shape for a chain.
+        // A kernel that stores to a peer cannot complete -- and its successor on the same stream
+        // cannot start -- before those stores have drained over NVLink: measured on 2 GPUs
+        // (profiles/r2_mg2f_exchange_timeline.jsonl) a 1.5 MB push takes 10 us from credit to
+        // publication and 4 more to the start of the next push behind it, against 2 us of
+        // payload time, whether it is the fused epilogue or a copy kernel.  Round trips cannot be
+        // shortened, so they are overlapped.
         if (k >= D) EPB_CUDA(cudaStreamWaitEvent(st, p->x_ev_push[(k - D) % D], 0));
-        rc = exchange_step(p, a, st, rec ? -2 : -1, nx, p->x_push, p->x_ev_step[k % D]);
+        cudaStream_t ps = p->x_push[k % 3];
+        rc = exchange_step(p, a, st, rec ? -2 : -1, nx, ps, p->x_ev_step[k % D]);
         if (rc != EPB_OK) return rc;
-        EPB_CUDA(cudaEventRecord(p->x_ev_push[k % D], p->x_push));
+        EPB_CUDA(cudaEventRecord(p->x_ev_push[k % D], ps));
         EPB_CUDA(cudaStreamWaitEvent(p->x_side, p->x_ev_push[k % D], 0));
         rc = exchange_wait_launch(p, p->x_side);
         if (rc != EPB_OK) return rc;
@@ -1337,7 +1356,7 @@ int epb_exchange_init(epb_pool* p, int world, int rank, void* ipc_handle_out) {
   }
   p->x_slice = p->slab_bytes + (((int64_t)4 * p->N + 255) / 256) * 256;
   p->x_data_off = (int64_t)p->x_depth * world * p->x_slice;
-  p->x_ack_off = p->x_data_off + 8 * kMaxPeers;
+  p->x_ack_off = p->x_data_off + 8 * kMaxPeers * kMaxDepth;
   p->x_ctl_off = p->x_ack_off + 8 * kMaxPeers;
   p->x_view_off = p->x_ctl_off + 256;
   p->x_bytes = p->x_view_off + (((int64_t)p->x_depth * sizeof(PeerView) + 255) / 256) * 256;
@@ -1357,6 +1376,21 @@ int epb_exchange_init(epb_pool* p, int world, int rank, void* ipc_handle_out) {
   if (const char* to = getenv("ENVPOOL_B200_EXCHANGE_TIMEOUT_S")) {
     double sec = atof(to);
     if (sec > 0) p->x_timeout_ns = (long long)(sec * 1e9);
+  }
+  {
+    ExchangeCtl c{};
+    for (int sl = 0; sl < p->x_depth; ++sl) c.slot_step[sl] = (unsigned long long)sl;
+    const char* tr = getenv("ENVPOOL_B200_EXCHANGE_TRACE");
+    if (tr && tr[0] == '1' && !p->x_trace) {
+      p->x_trace_steps = 1 << 16;
+      EPB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->x_trace),
+                          (size_t)p->x_trace_steps * 8 * sizeof(long long)));
+      EPB_CUDA(cudaMemset(p->x_trace, 0, (size_t)p->x_trace_steps * 8 * sizeof(long long)));
+    }
+    c.trace = p->x_trace;
+    c.trace_steps = p->x_trace_steps;
+    static_assert(sizeof(ExchangeCtl) <= 256, "ctl block is 256 bytes");
+    EPB_CUDA(cudaMemcpy(p->x_base + p->x_ctl_off, &c, sizeof(c), cudaMemcpyHostToDevice));
   }
   if (world == 1) {
     int rc = upload_views(p);
@@ -1508,6 +1542,15 @@ int epb_exchange_wait(epb_pool* p, void* stream, void** d_gathered) {
   int rc = exchange_wait_launch(p, s);
   if (rc != EPB_OK) return rc;
   if (d_gathered) *d_gathered = p->x_base + (int64_t)slot * p->x_world * p->x_slice;
+  return EPB_OK;
+}
+int epb_exchange_trace(epb_pool* p, int64_t* out, int64_t steps) {
+  if (!p || !p->x_base || !p->x_trace) return fail(EPB_ERR_STATE, "exchange trace is off");
+  DeviceGuard guard(p->cfg.device);
+  EPB_CUDA(guard.status);
+  if (steps > p->x_trace_steps) steps = p->x_trace_steps;
+  EPB_CUDA(cudaMemcpy(out, p->x_trace, (size_t)steps * 8 * sizeof(long long),
+                      cudaMemcpyDeviceToHost));
   return EPB_OK;
 }
 int epb_exchange_status(epb_pool* p, int64_t* steps_pushed, int* timed_out) {

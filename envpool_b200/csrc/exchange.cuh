@@ -3,7 +3,7 @@
 // The reference has no counterpart (it is single-process); north_star asks that after every
 // step each GPU holds the outputs of ALL envs.  Every rank owns one "gather" allocation
 //
-//     slot[D][world][slice_bytes] | data_flag[16] | ack_flag[16] | ctl | PeerView[D]
+//     slot[D][world][slice_bytes] | data_flag[D][16] | ack_flag[16] | ctl | PeerView[D]
 //
 // mapped into every peer (CUDA IPC between processes, plain pointers inside one process).
 // slice = the packed output slab (all 13 columns at their slab offsets) + one extra "wire"
@@ -48,13 +48,36 @@ constexpr int kMaxDepth = 8;
 constexpr int kMaxCols = 13;  // 8 common state keys + at most 5 env keys (OutView::env)
 
 struct ExchangeCtl {
-  unsigned int blocks_done;    // last-block-done counter of the publishing kernel
-  unsigned int wait_blocks;    // ... and of the wait kernel
-  unsigned long long seq;      // steps pushed by this rank
+  unsigned int blocks_done[kMaxDepth];       // last-block-done counter of the push into slot s
+  unsigned int wait_blocks;                  // ... and of the wait kernel
+  unsigned int pad0;
+  // step index the NEXT push into ring slot s carries (s, s + D, s + 2D, ...): pushes into
+  // different slots may be in flight together (captured chains run them on several branches),
+  // so the step a pushing kernel works on cannot be a single running counter
+  unsigned long long slot_step[kMaxDepth];
+  unsigned long long seq;      // steps published by this rank (highest step + 1)
   unsigned long long waited;   // steps whose wait kernel has finished on this rank
   int error;                   // 1 = a wait timed out
   int pad2;
+  // optional timeline (ENVPOOL_B200_EXCHANGE_TRACE=1; profiles/exchange_trace.py): 8 globaltimer
+  // stamps per exchanged step: [0] push kernel starts, [1] its credit is there, [2] its last
+  // CTA publishes, [3] wait kernel starts, [4] last peer flag seen, [5] wait kernel ends
+  long long* trace;
+  long long trace_steps;
 };
+__device__ __forceinline__ long long exchange_now() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void exchange_stamp(ExchangeCtl* ctl, unsigned long long step, int k,
+                                               bool take_max = false) {
+  if (ctl->trace && (long long)step < ctl->trace_steps) {
+    long long* p = ctl->trace + step * 8 + k;
+    if (take_max) atomicMax(p, exchange_now());
+    else *p = exchange_now();
+  }
+}
 
 struct PeerView {
   char* slice[kMaxPeers];                // slot[s][rank] in the allocation of rank g
@@ -65,6 +88,7 @@ struct PeerView {
   int world;
   int rank;
   int depth;                             // ring slots
+  int slot;                              // the ring slot this view describes
   // wire columns (forwarded to peers): byte offset in the slice and bytes per row
   int ncols;
   int col_rb[kMaxCols];
@@ -89,18 +113,18 @@ __device__ __forceinline__ int32_t pack_wire(int cur, int done, int trunc) {
   return (cur << 2) | (trunc << 1) | done;
 }
 
-// Credit of step t (t = ctl->seq, the steps this rank has pushed so far): slot t % D may be
+// Credit of step t (t = ctl->slot_step[slot], the step this push into the slot carries): slot t % D may be
 // overwritten on rank g once g has released step t - D, i.e. ack_flag[g] >= t - D + 1.  The
 // flags live in THIS rank's memory (peers store into them), so the poll is a local L2 read
 // and, with any slack in the ring, true on the first look.  Lanes 0..world-1 of the CTA poll;
-// bounded like every wait of the exchange.  ctl->seq cannot change while a CTA is here: it
-// is bumped by the last CTA to finish, and this one has not finished.  Deadlock-free: the
+// bounded like every wait of the exchange.  slot_step[slot] cannot change while a CTA is here:
+// it is bumped by the last CTA of this push to finish, and this one has not finished.  Deadlock-free: the
 // releases a rank waits for are published by kernels of OTHER GPUs, and its own release of
 // step t - D precedes this kernel in stream / graph order.
 __device__ __forceinline__ void peer_credit(const PeerView* __restrict__ pv) {
   const int tid = threadIdx.x;
   if (tid < pv->world) {  // own release included: the local consumer may sit on another stream
-    const unsigned long long t = pv->ctl->seq;
+    const unsigned long long t = pv->ctl->slot_step[pv->slot];
     if (t >= (unsigned long long)pv->depth) {
       const unsigned long long need = t - pv->depth + 1;
       long long t0 = 0;
@@ -129,21 +153,24 @@ __device__ __forceinline__ void peer_credit(const PeerView* __restrict__ pv) {
 // in-flight NVLink stores was the dominant cost of a small exchange (a 1.5 MB CartPole push took
 // ~14 us, payload time 2 us).  The CTA that completes the count bumps the sequence number,
 // fences once more (acquire side of the ticket, release side of the flags) and raises
-// data_flag[rank] on every rank with relaxed stores (a release per flag would pay one NVLink
+// data_flag[slot][rank] = step + 1 on every rank with relaxed stores (a release per flag would pay one NVLink
 // round trip per peer).  Call with all threads of the CTA.
 __device__ __forceinline__ void peer_publish(const PeerView* __restrict__ pv) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
     ExchangeCtl* ctl = pv->ctl;
-    unsigned int ticket = atomicAdd(&ctl->blocks_done, 1u);
+    const int slot = pv->slot;
+    unsigned int ticket = atomicAdd(&ctl->blocks_done[slot], 1u);
     if (ticket == gridDim.x - 1) {
-      ctl->blocks_done = 0;
-      unsigned long long s = ctl->seq + 1;
-      ctl->seq = s;
+      ctl->blocks_done[slot] = 0;
+      const unsigned long long t = ctl->slot_step[slot];
+      exchange_stamp(ctl, t, 2);
+      ctl->slot_step[slot] = t + pv->depth;
+      atomicMax(&ctl->seq, t + 1);
       __threadfence_system();
       const int world = pv->world;
-      for (int g = 0; g < world; ++g) st_relaxed_sys(pv->flag[g], s);
+      for (int g = 0; g < world; ++g) st_relaxed_sys(pv->flag[g], t + 1);
     }
   }
 }
