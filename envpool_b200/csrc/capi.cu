@@ -741,8 +741,6 @@ int epb_create(int kind, const epb_config* cfg, epb_pool** out) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->mark_side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->x_side, cudaStreamNonBlocking);
-  for (cudaStream_t& ps : p->x_push)
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_mark, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&p->ev_t0);
   if (e == cudaSuccess) e = cudaEventCreate(&p->ev_t1);
@@ -1253,6 +1251,11 @@ int chain_entry(epb_pool* p, const void* d_actions, int T_stream, int t0, int K,
   DeviceGuard guard(p->cfg.device);
   EPB_CUDA(guard.status);
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : p->stream;
+  if (exchange && use_graph && p->x_side_push && !p->x_push[0]) {
+    // push branches of the captured exchange chains: created on first use (a pool that never
+    // captures one never holds them -- streams map onto a bounded set of hardware queues)
+    for (cudaStream_t& ps : p->x_push) EPB_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+  }
   if (p->refill_fn && p->since_refill > 0) {  // chains start from full record rings
     int rc = launch_refill(p, s);
     if (rc != EPB_OK) return rc;
