@@ -259,8 +259,8 @@ def wire_bytes_per_env(pool):
 
 def measure_exchange(torch, dist, timer, pool, world, rank, dev, K, lead):
     """`K` exchanged steps (step -> wire columns into every peer -> flags -> receiver-side
-    re-expansion), waits on a parallel graph branch: up to depth-1 steps run ahead of the
-    batch that is still arriving.  A step counts as complete when its batch has arrived."""
+    re-expansion), pushes and waits on parallel graph branches: up to depth-1 steps run ahead of
+    the batch that is still arriving.  A step counts as complete when its batch has arrived."""
     err = attach_exchange(torch, dist, pool, world, rank, dev)
     if err:
         return {"unavailable": err}
@@ -280,10 +280,11 @@ def measure_exchange(torch, dist, timer, pool, world, rank, dev, K, lead):
             "nvlink_gbs_in_per_gpu": wire * K / (ms * 1e-3) / 1e9,
             "wire_bytes_per_env_step": wire_bytes_per_env(pool),
             "ring_depth": pool.exchange_depth,
-            "api": "epb_step_exchange_many_device: per step the step kernel (writes its slice, "
-                   "checks the ring credit, forwards env keys + reward + packed word to every "
-                   "peer over NVLink, publishes) and one wait kernel (acquires every peer's "
-                   "flag, re-expands the common columns); CUDA-graph replay, waits and record "
+            "api": "epb_step_exchange_many_device: per step the step kernel (writes its slice into "
+                   "its ring slot), one push kernel on one of three push branches (checks the ring "
+                   "credit, forwards env keys + reward + packed word to every peer over NVLink, "
+                   "publishes the slot's flag) and one wait kernel (acquires every peer's flag, "
+                   "re-expands the common columns); CUDA-graph replay; pushes, waits and record "
                    "refills on parallel branches"}
 
 

@@ -27,8 +27,8 @@ def phase_ranges(src):
             marks.append((i, "solve: Ma, row pass (H, force, cost), grad"))
         if "pair_factor(c, H, FH)" in ln:
             marks.append((i, "solve: factor H, apply, Mv, Jv"))
-        if re.search(r"for \(int k = 0; k < cm.ls_iter", ln):
-            marks.append((i, "solve: line search"))
+        if "const double gtol = cm.tolerance" in ln:
+            marks.append((i, "solve: line search (first pass fused with J*search)"))
     return sorted(marks)
 
 
