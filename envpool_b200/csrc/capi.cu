@@ -355,13 +355,27 @@ push_kernel(const PeerView* __restrict__ pv, int n) {
   for (int k = 0; k < pv->ncols; ++k) {
     const int64_t off = pv->col_off[k];
     const int64_t n16 = ((int64_t)n * pv->col_rb[k] + 15) >> 4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
-      uint4 v = reinterpret_cast<const uint4*>(src + off)[i];
+    // up to four 16-byte units per thread and pass: the loads (L2 hits) first, then the stores
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n16; i0 += 4 * stride) {
+      uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t i = i0 + j * stride;
+        if (i < n16) v[j] = reinterpret_cast<const uint4*>(src + off)[i];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t i = i0 + j * stride;
+        if (i < n16) {
 #pragma unroll 1
-      for (int g = 0; g < world; ++g)
-        if (g != rank) reinterpret_cast<uint4*>(pv->slice[g] + off)[i] = v;
+          for (int g = 0; g < world; ++g)
+            if (g != rank) reinterpret_cast<uint4*>(pv->slice[g] + off)[i] = v[j];
+        }
+      }
     }
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    exchange_stamp(pv->ctl, pv->ctl->slot_step[pv->slot], 6);
   peer_publish(pv);
 }
 
@@ -1478,8 +1492,15 @@ int exchange_step(epb_pool* p, const void* d_action, cudaStream_t s, int chain_k
     int64_t n16 = 0;
     for (size_t k = 8; k < p->keys.size(); ++k)
       n16 += ((int64_t)p->N * p->keys[k].row_bytes + 15) / 16;
+    // CTAs of the copy kernel: one 16-byte unit per thread and pass, at most 8 CTAs per SM
+    // (ENVPOOL_B200_PUSH_CTAS caps it lower: every CTA ends in a system-scope fence)
+    static const int64_t cta_cap = [] {
+      const char* e = getenv("ENVPOOL_B200_PUSH_CTAS");
+      const int v = e ? atoi(e) : 0;
+      return (int64_t)(v > 0 ? v : 148 * 8);
+    }();
     int64_t blocks = (n16 + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > cta_cap) blocks = cta_cap;
     if (blocks < 1) blocks = 1;
     push_kernel<<<(unsigned)blocks, 256, 0, s>>>(p->x_view(slot), p->N);
     EPB_CUDA(cudaGetLastError());

@@ -61,7 +61,8 @@ struct ExchangeCtl {
   int pad2;
   // optional timeline (ENVPOOL_B200_EXCHANGE_TRACE=1; profiles/exchange_trace.py): 8 globaltimer
   // stamps per exchanged step: [0] push kernel starts, [1] its credit is there, [2] its last
-  // CTA publishes, [3] wait kernel starts, [4] last peer flag seen, [5] wait kernel ends
+  // CTA publishes, [3] wait kernel starts, [4] last peer flag seen, [5] wait kernel ends,
+  // [6] CTA 0 of the push has issued its stores, [7] CTA 0 is past its system fence
   long long* trace;
   long long trace_steps;
 };
@@ -161,6 +162,7 @@ __device__ __forceinline__ void peer_publish(const PeerView* __restrict__ pv) {
     __threadfence_system();
     ExchangeCtl* ctl = pv->ctl;
     const int slot = pv->slot;
+    if (blockIdx.x == 0) exchange_stamp(ctl, ctl->slot_step[slot], 7);
     unsigned int ticket = atomicAdd(&ctl->blocks_done[slot], 1u);
     if (ticket == gridDim.x - 1) {
       ctl->blocks_done[slot] = 0;

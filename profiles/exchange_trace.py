@@ -40,13 +40,15 @@ def main():
         dist.barrier()
         ms_ = pool.step_many_timed(actions, 0, lead + K, lead, lead + K, True, True)
     first = 1 + 2 * (lead + K) + lead       # exchanged steps before the timed window of replay 3
-    tr = pool.exchange_trace(first + K).astype(np.float64)[first:first + K, :6]
+    tr = pool.exchange_trace(first + K).astype(np.float64)[first:first + K, :8]
     t0 = tr[tr > 0].min()
     rel = np.where(tr > 0, (tr - t0) / 1e3, -1.0)
     print(json.dumps({"rank": rank, "task": task, "n": n, "us_per_step": round(ms_ / K * 1e3, 2),
                       "mode": os.environ.get("ENVPOOL_B200_EXCHANGE_CHAIN", "side"),
+                      "depth": os.environ.get("ENVPOOL_B200_EXCHANGE_DEPTH", "4"),
+                      "push_ctas": os.environ.get("ENVPOOL_B200_PUSH_CTAS", "default"),
                       "cols": ["push_start", "push_credit", "push_publish", "wait_start",
-                               "wait_flag", "wait_end"],
+                               "wait_flag", "wait_end", "push_cta0_stored", "push_cta0_fenced"],
                       "rows_us": [[round(float(v), 1) for v in r] for r in rel]}), flush=True)
     dist.barrier()
     pool.close()
