@@ -1489,17 +1489,20 @@ int exchange_step(epb_pool* p, const void* d_action, cudaStream_t s, int chain_k
       EPB_CUDA(cudaStreamWaitEvent(push_stream, step_done, 0));
       s = push_stream;
     }
-    int64_t n16 = 0;
-    for (size_t k = 8; k < p->keys.size(); ++k)
-      n16 += ((int64_t)p->N * p->keys[k].row_bytes + 15) / 16;
-    // CTAs of the copy kernel: one 16-byte unit per thread and pass, at most 8 CTAs per SM
-    // (ENVPOOL_B200_PUSH_CTAS caps it lower: every CTA ends in a system-scope fence)
+    // CTAs of the copy kernel: eight 16-byte units per thread (two passes of four), at most 8
+    // CTAs per SM.  Every CTA ends in a system-scope fence, and on two GPUs the fence phase of a
+    // 1.5 MB push measured 5.9 us with 256 CTAs, 3.7 with 64, 3.3 with 16 (where the stores
+    // themselves then took 5.7 us): 13.5 / 9.5 / 10.3 us per exchanged step
+    // (profiles/r2_mg2h_exchange_timeline.jsonl).  ENVPOOL_B200_PUSH_CTAS overrides.
     static const int64_t cta_cap = [] {
       const char* e = getenv("ENVPOOL_B200_PUSH_CTAS");
       const int v = e ? atoi(e) : 0;
       return (int64_t)(v > 0 ? v : 148 * 8);
     }();
-    int64_t blocks = (n16 + 255) / 256;
+    int64_t n16 = ((int64_t)p->N * 4 + 15) / 16 * 2;  // reward + the packed word
+    for (size_t k = 8; k < p->keys.size(); ++k)
+      n16 += ((int64_t)p->N * p->keys[k].row_bytes + 15) / 16;
+    int64_t blocks = (n16 + 2047) / 2048;
     if (blocks > cta_cap) blocks = cta_cap;
     if (blocks < 1) blocks = 1;
     push_kernel<<<(unsigned)blocks, 256, 0, s>>>(p->x_view(slot), p->N);
