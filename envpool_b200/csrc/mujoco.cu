@@ -1,4 +1,4 @@
-// HalfCheetah (mujoco/gym) family: ONE WARP PER ENV.  The reference's per-env Step() is
+// HalfCheetah (mujoco/gym) family.  The reference's per-env Step() is
 //   ctrl <- action; mj_step x frame_skip        (envpool/mujoco/gym/mujoco_env.h:137-148)
 //   reward / obs / infos from qpos, qvel        (envpool/mujoco/gym/half_cheetah.h:136-185)
 // with all physics inside MuJoCo 3.6.0 (third-party, not vendored).  This file is a
@@ -8,15 +8,19 @@
 // joint-limit + pyramidal-contact constraint rows, Newton solver with exact line search on
 // the convex primal problem, semi-implicit Euler with implicit joint damping.
 //
-// Mapping: lanes are bodies (kinematics), matrix entries (inertia, Hessian), candidate
-// contacts / limits (collision), constraint rows (solver); the 9x9 systems, the row table
-// and all per-step vectors live in shared memory (9 KB per warp), reductions are warp
-// shuffles, env state (qpos, qvel, qacc_warmstart: 27 doubles) is loaded and stored once per
-// env step as one contiguous 256 B record.  Arithmetic is fp64 (B200 keeps a full-rate FP64
-// pipe); there is no dense contraction here, so no tensor cores.
+// Three kernels, selected by ENVPOOL_B200_HC_KERNEL at pool creation:
+//   pair   (default)  two lanes per env, mujoco_pair.cuh -- hc_pair_kernel below
+//   thread            one thread per env, mujoco_thread.cuh -- hc_thread_kernel (round-1 default)
+//   warp              one warp per env, this file -- hc_kernel: lanes are bodies (kinematics),
+//                     matrix entries (inertia, Hessian), candidate contacts / limits (collision),
+//                     constraint rows (solver); 9x9 systems, row table and per-step vectors in
+//                     shared memory (9 KB per warp), warp-shuffle reductions.  What north_star
+//                     suggested; 9x slower than thread-per-env because nv = 9 cannot feed 32 lanes.
+// Host side of the file: compile_half_cheetah (what mj_loadXML derives from the XML) and the
+// launch plumbing.  Arithmetic is fp64 (the reference's); no dense contraction, no tensor cores.
 //
-// PARITY: unpinned against MuJoCo itself (absent from the image); pinned against the CPU
-// restatement of the same pipeline (tests/ only).  See DESIGN.md "HalfCheetah".
+// PARITY: unpinned against MuJoCo itself (absent from the image and from the GPU box); pinned
+// against the CPU restatement of the same pipeline (tests/ only).  See DESIGN.md section 3.
 #include "mujoco.cuh"
 #include "mujoco_model.h"
 
