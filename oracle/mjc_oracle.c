@@ -630,6 +630,32 @@ double mjc_debug_dynamics(const mjc_model* m, const double* qpos, const double* 
   return V;
 }
 
+/* Diagnostics for tests/test_mjc_oracle.py: the constraint problem of the current state as the
+ * solver sees it -- M (row-major NVxNV), qfrc_smooth, the rows (J row-major [n][NV], D, aref)
+ * -- and the solver's answer qacc, so that an independent optimiser can be run on the same
+ * convex cost  1/2 (a - a_s)' M (a - a_s) + sum_i 1/2 D_i min(0, J_i a - aref_i)^2.  Returns the
+ * number of rows (at most cap_rows are written). */
+int mjc_debug_solve(const mjc_model* m, mjc_data* d, double* M_out, double* qfrc_smooth_out,
+                    double* J_out, double* D_out, double* aref_out, int cap_rows,
+                    double* qacc_out) {
+  double org[NB][2], th[NB], com[NB][2];
+  double M[NV * NV], fs[NV], fc[NV];
+  static efc_t e;
+  int ncon = 0;
+  forward(m, d, M, fs, fc);
+  kinematics(m, d->qpos, org, th, com);
+  make_constraints(m, d->qpos, d->qvel, org, th, &e, &ncon);
+  memcpy(M_out, M, sizeof(M));
+  memcpy(qfrc_smooth_out, fs, sizeof(fs));
+  memcpy(qacc_out, d->qacc, sizeof(double) * NV);
+  for (int r = 0; r < e.n && r < cap_rows; ++r) {
+    memcpy(J_out + r * NV, e.J[r], sizeof(double) * NV);
+    D_out[r] = e.D[r];
+    aref_out[r] = e.aref[r];
+  }
+  return e.n;
+}
+
 void mjc_forward(const mjc_model* m, mjc_data* d) {
   double M[NV * NV], fs[NV], fc[NV];
   forward(m, d, M, fs, fc);

@@ -38,6 +38,9 @@ int mjc_nefc(const mjc_data* d);
 int mjc_model_constants(const mjc_model* m, double* out, int cap);
 
 /* M(q) [81], bias(q, qvel) [9] (either may be NULL); returns the gravitational potential */
+int mjc_debug_solve(const mjc_model* m, mjc_data* d, double* M_out, double* qfrc_smooth_out,
+                    double* J_out, double* D_out, double* aref_out, int cap_rows,
+                    double* qacc_out);
 double mjc_debug_dynamics(const mjc_model* m, const double* qpos, const double* qvel,
                           double* M_out, double* bias_out);
 

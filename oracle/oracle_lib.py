@@ -227,6 +227,19 @@ class MjcSim:
                                       c.ctypes.data)
         return M, c, V
 
+    def solve_problem(self):
+        """Runs the forward dynamics of the current state and returns the constraint problem as
+        the solver sees it plus its answer: dict(M, qfrc_smooth, J, D, aref, qacc)."""
+        vp = ctypes.c_void_p
+        self.L.mjc_debug_solve.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        cap = 80
+        M, fs, qacc = np.zeros((9, 9)), np.zeros(9), np.zeros(9)
+        J, D, aref = np.zeros((cap, 9)), np.zeros(cap), np.zeros(cap)
+        n = self.L.mjc_debug_solve(self.m, self.d, M.ctypes.data, fs.ctypes.data, J.ctypes.data,
+                                   D.ctypes.data, aref.ctypes.data, cap, qacc.ctypes.data)
+        return {"M": M, "qfrc_smooth": fs, "J": J[:n].copy(), "D": D[:n].copy(),
+                "aref": aref[:n].copy(), "qacc": qacc}
+
     def constants(self):
         buf = np.zeros(64)
         n = self.L.mjc_model_constants(self.m, buf.ctypes.data, 64)

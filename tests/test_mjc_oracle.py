@@ -144,3 +144,53 @@ def test_bias_force_satisfies_lagranges_equations(sim):
     total = sim.constants()["mass"].sum()
     assert abs(M0[0, 0] - total) < 1e-12 and abs(M0[1, 1] - total) < 1e-12
     assert abs(M0[0, 1]) < 1e-12
+
+
+def test_newton_solver_reaches_the_minimiser_of_the_stated_problem(sim):
+    """The constraint solve is a convex program: qacc = argmin_a 1/2 (a - a_s)' M (a - a_s) +
+    sum_i 1/2 D_i min(0, J_i a - aref_i)^2.  An independent optimiser (scipy, trust-region
+    Newton on the exact gradient / Hessian of that cost) started from qacc_smooth must land on the
+    restatement's answer, and the answer must satisfy the optimality condition -- which pins
+    the hand-written Newton iteration, its line search and its stopping rules (what the CUDA
+    kernels restate once more) to the problem they claim to solve.  States: contact-rich
+    (folded legs near the floor, fast) with joint limits active."""
+    from scipy.optimize import minimize
+
+    rng = np.random.default_rng(11)
+    checked = 0
+    for trial in range(60):
+        sim.qpos[:] = rng.uniform(-0.1, 0.1, 9)
+        sim.qpos[1] = rng.uniform(-0.25, 0.2)
+        sim.qpos[2] = rng.uniform(-1.5, 1.5)
+        sim.qpos[3:] = rng.uniform(-1.3, 1.3, 6)
+        sim.qvel[:] = rng.normal(0, 2.0, 9)
+        p = sim.solve_problem()
+        M, J, D, aref = p["M"], p["J"], p["D"], p["aref"]
+        if len(D) == 0:
+            continue
+        a_s = np.linalg.solve(M, p["qfrc_smooth"])
+
+        def cost(a):
+            r = np.minimum(0.0, J @ a - aref)
+            da = a - a_s
+            return 0.5 * da @ M @ da + 0.5 * np.sum(D * r * r)
+
+        def grad(a):
+            r = np.minimum(0.0, J @ a - aref)
+            return M @ (a - a_s) + J.T @ (D * r)
+
+        def hess(a):
+            act = (J @ a - aref) < 0
+            return M + (J[act].T * D[act]) @ J[act]
+
+        a = p["qacc"]
+        scale = 1.0 / (np.trace(M) / 9 * 9)   # the solver's own scaling of its tolerances
+        g = grad(a)
+        assert scale * np.linalg.norm(g) < 1e-6, (trial, len(D), scale * np.linalg.norm(g))
+        ref = minimize(cost, a_s, jac=grad, hess=hess, method="trust-exact",
+                       options={"gtol": 1e-12, "maxiter": 500})
+        assert cost(a) <= ref.fun * (1 + 1e-9) + 1e-9, (trial, cost(a), ref.fun)
+        assert np.linalg.norm(a - ref.x) <= 1e-6 * (1 + np.linalg.norm(ref.x)), (
+            trial, len(D), np.linalg.norm(a - ref.x))
+        checked += 1
+    assert checked >= 40, checked
