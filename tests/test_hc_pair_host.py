@@ -93,3 +93,25 @@ def test_model_blob_matches_oracle_constants():
     np.testing.assert_allclose(d[142:149], c["body_invweight0"][:, 0], rtol=1e-11)
     np.testing.assert_allclose(d[153], c["meaninertia"], rtol=1e-13)
     assert d[149] == 0.046 and d[150] == 0.01 and d[151] == -9.81 and d[152] == 0.4
+
+
+def test_row_storage_does_not_change_the_arithmetic(pair_host):
+    """Rows in the shared-memory slab or in the thread-local overflow: same values, bit for bit
+    (ks = 27: all rows in the slab; ks = 0 / 3: all / most rows in the overflow)."""
+    from envpool_b200 import _capi
+
+    blob = _capi.hc_model_blob()
+    rng = np.random.default_rng(7)
+    for _ in range(40):
+        q0 = rng.uniform(-0.1, 0.1, 9)
+        q0[1] = rng.uniform(-0.25, 0.2)
+        q0[2] = rng.uniform(-1.5, 1.5)
+        q0[3:] = rng.uniform(-1.3, 1.3, 6)
+        v0, w0, a = rng.normal(0, 2.0, 9), rng.normal(0, 3.0, 9), rng.uniform(-1, 1, 6)
+        outs = []
+        for ks in (27, 3, 0):
+            q, v, w = q0.copy(), v0.copy(), w0.copy()
+            assert pair_host.hc_pair_host_step(blob, q.ctypes.data, v.ctypes.data, w.ctypes.data,
+                                               a.ctypes.data, 5, ks) == 0
+            outs.append(np.concatenate([q, v, w]))
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
